@@ -1,0 +1,254 @@
+/* sgc_b200.h — C ABI of libsgc_b200.so: the B200-native replacement for the two data-parallel
+ * hot paths of wsshin/StaggeredGridCalculus.jl (matrix-free staggered-grid operators and
+ * sparse-operator assembly).
+ *
+ * The reference has no FFI: its boundary is Julia multiple dispatch on the concrete methods
+ * cited next to each entry point below (paths relative to the reference's src/).  A Julia shim
+ * (staggeredgridcalculus.jl_b200/julia/SGCB200.jl) adds methods with the
+ * same signatures on a device-array type and forwards them here through `ccall`; the Python
+ * `ctypes` mirror in staggeredgridcalculus.jl_b200/ binds exactly the same symbols.
+ *
+ * Conventions
+ *  - Plain C types only.  Every function returns an `int` status (SGC_OK == 0); the message of
+ *    the last failure on the calling thread is returned by sgc_last_error().
+ *  - Field arrays (`G`, `F`, `Gv`, `Fu`, `g`, `f`) are DEVICE pointers to column-major Julia
+ *    arrays: F[i,j,k,w] with the component index w last (slowest), i.e. K contiguous
+ *    component planes of prod(N) elements.  dtype SGC_F64 = Float64, SGC_C128 = ComplexF64
+ *    (re,im interleaved).  The `*_host` variants take HOST pointers and do the copies.
+ *  - Per-axis coefficient vectors (∆w⁻¹, ∆w, ∆w′⁻¹) are HOST pointers to N[w] elements of
+ *    Float64 (`coef_complex == 0`) or ComplexF64 (`coef_complex == 1`); they are O(ΣN) and are
+ *    turned into resident device tables when an operator handle is created.
+ *  - Scalars e⁻ⁱᵏᴸ and α are passed as (re, im) pairs of doubles.
+ *  - Axis numbers `nw`, components `cmp_*` are 1-based, exactly as in the reference.
+ *  - `op`: SGC_OP_SET is Val(:(=)), SGC_OP_ADD is Val(:(+=))  (matrixfree/matrixfree.jl:6-8).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Calls are
+ *    asynchronous with respect to the host unless stated otherwise.
+ *  - No CPU fallback exists: without a CUDA device every compute entry point fails with
+ *    SGC_ERR_CUDA.
+ */
+#ifndef SGC_B200_H
+#define SGC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGC_ABI_VERSION 1
+
+/* status codes */
+#define SGC_OK 0
+#define SGC_ERR_INVALID 1 /* the reference's @assert / @error conditions */
+#define SGC_ERR_CUDA 2    /* CUDA runtime failure, or no device */
+#define SGC_ERR_INEXACT 3 /* complex α / e / ∆ with a Float64 field (Julia InexactError) */
+#define SGC_ERR_NOMEM 4
+
+/* element types */
+#define SGC_F64 0
+#define SGC_C128 1
+
+/* set_or_add! */
+#define SGC_OP_SET 0
+#define SGC_OP_ADD 1
+
+/* ---------------------------------------------------------------------------------------- */
+/* library / device plumbing                                                                */
+/* ---------------------------------------------------------------------------------------- */
+int sgc_abi_version(void);
+const char *sgc_last_error(void);
+int sgc_device_count(int *count);
+int sgc_set_device(int device);
+int sgc_malloc(void **dptr, size_t bytes);
+int sgc_free(void *dptr);
+int sgc_malloc_host(void **hptr, size_t bytes); /* pinned */
+int sgc_free_host(void *hptr);
+int sgc_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+int sgc_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+int sgc_memset_zero(void *dptr, size_t bytes, void *stream);
+int sgc_stream_create(void **stream);
+int sgc_stream_destroy(void *stream);
+int sgc_stream_sync(void *stream);
+/* Number of kernels this library has launched on the calling process so far (bench.py's
+ * `gpu_launches` evidence). */
+int64_t sgc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Matrix-free operators: operator handles                                                  */
+/* An sgc_op owns the device-resident per-axis tables (α·∆w⁻¹ etc.) of one operator so that  */
+/* repeated application (solver iterations, CUDA-graph capture) does no host work.           */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct sgc_op sgc_op;
+
+/* apply_∂!  — matrixfree/differential/partial.jl:33 (3-D), :241 (2-D), :388 (1-D); the
+ * scalar-∆ wrapper :11-21 is `fill` on the caller's side. */
+int sgc_op_create_partial(sgc_op **op, int dtype, int ndim, const int64_t *N, int nw, int isfwd,
+                          const void *dwinv, int coef_complex, int isbloch, const double *e,
+                          const double *alpha);
+
+/* apply_m̂!  — matrixfree/mean.jl:102/295/432 (arithmetic: dw == dwpinv == NULL) and
+ * :493/705/856 (weighted). */
+int sgc_op_create_mhat(sgc_op **op, int dtype, int ndim, const int64_t *N, int nw, int isfwd,
+                       const void *dw, const void *dwpinv, int coef_complex, int isbloch,
+                       const double *e, const double *alpha);
+
+/* apply_curl!  — matrixfree/differential/curl.jl:52-137 (wrappers :12-49).  `dlinv[d]` is the
+ * vector of array dimension d (length N[d]); `e` holds ndim (re,im) pairs; cmp_shp has ndim
+ * entries, cmp_out Kout, cmp_in Kin.  The full 3-D curl (cmp_shp = cmp_out = cmp_in = 1:3)
+ * runs as ONE fused kernel; sub-curls run as per-block sweeps. */
+int sgc_op_create_curl(sgc_op **op, int dtype, int ndim, const int64_t *N, const int *isfwd,
+                       const void *const *dlinv, int coef_complex, const int *isbloch,
+                       const double *e, const int *cmp_shp, int Kout, const int *cmp_out, int Kin,
+                       const int *cmp_in, const double *alpha);
+
+/* apply_divg!  — matrixfree/differential/divergence.jl:41-66.  F has ndim components. */
+int sgc_op_create_divg(sgc_op **op, int dtype, int ndim, const int64_t *N, const int *isfwd,
+                       const void *const *dlinv, int coef_complex, const int *isbloch,
+                       const double *e, const double *alpha);
+
+/* apply_grad!  — matrixfree/differential/gradient.jl:41-59.  G has ndim components. */
+int sgc_op_create_grad(sgc_op **op, int dtype, int ndim, const int64_t *N, const int *isfwd,
+                       const void *const *dlinv, int coef_complex, const int *isbloch,
+                       const double *e, const double *alpha);
+
+/* apply_mean!  — matrixfree/mean.jl:47-65 (arithmetic: dl == dlpinv == NULL), :69-89. */
+int sgc_op_create_mean(sgc_op **op, int dtype, int ndim, const int64_t *N, const int *isfwd,
+                       const void *const *dl, const void *const *dlpinv, int coef_complex,
+                       const int *isbloch, const double *e, const double *alpha);
+
+/* z-slab mode (multi-GPU): N given at creation is the LOCAL slab; the last
+ * array dimension is the decomposed one.  `lo_interface` / `hi_interface` != 0 mark the slab
+ * face as an interior interface (the neighbour plane comes from another rank, no boundary
+ * condition is applied there) instead of a physical boundary. */
+int sgc_op_set_slab(sgc_op *op, int lo_interface, int hi_interface);
+
+/* Kernel tuning knobs (0 keeps the default): tile size and z-march length of the fused curl. */
+int sgc_op_set_tuning(sgc_op *op, int tile_x, int tile_y, int march_z, int variant);
+
+/* G OP α·(operator)(F).  Returns immediately; work is queued on `stream`. */
+int sgc_op_apply(const sgc_op *op, void *G, const void *F, int opmode, void *stream);
+
+/* Same, restricted to the planes [k_begin, k_end) of the last array dimension, with the
+ * ghost plane(s) of the input taken from `ghost[c]` (one DEVICE pointer per input component
+ * c, each to prod(N[0..ndim-2]) elements; NULL where the operator needs none or where the
+ * plane lives in F itself).  For a physical Bloch face the ghost plane holds the RAW values
+ * of the wrap-around plane; the kernel applies e⁻ⁱᵏᴸ (forward) or divides by it (backward)
+ * exactly as partial.jl:140 / :226 do.  `ghost` pointers may be peer (NVLink) addresses. */
+int sgc_op_apply_range(const sgc_op *op, void *G, const void *F, int opmode,
+                       const void *const *ghost, int64_t k_begin, int64_t k_end, void *stream);
+
+int sgc_op_destroy(sgc_op *op);
+
+/* Number of kernel launches one sgc_op_apply of this operator issues. */
+int sgc_op_launches(const sgc_op *op, int opmode);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Matrix-free operators: one-shot calls with the reference's argument lists (create a       */
+/* transient handle, apply, destroy).                                                        */
+/* ---------------------------------------------------------------------------------------- */
+int sgc_apply_partial(void *Gv, const void *Fu, int opmode, int dtype, int ndim, const int64_t *N,
+                      int nw, int isfwd, const void *dwinv, int coef_complex, int isbloch,
+                      const double *e, const double *alpha, void *stream);
+int sgc_apply_mhat(void *Gv, const void *Fu, int opmode, int dtype, int ndim, const int64_t *N,
+                   int nw, int isfwd, const void *dw, const void *dwpinv, int coef_complex,
+                   int isbloch, const double *e, const double *alpha, void *stream);
+int sgc_apply_curl(void *G, const void *F, int opmode, int dtype, int ndim, const int64_t *N,
+                   const int *isfwd, const void *const *dlinv, int coef_complex,
+                   const int *isbloch, const double *e, const int *cmp_shp, int Kout,
+                   const int *cmp_out, int Kin, const int *cmp_in, const double *alpha,
+                   void *stream);
+int sgc_apply_divg(void *g, const void *F, int opmode, int dtype, int ndim, const int64_t *N,
+                   const int *isfwd, const void *const *dlinv, int coef_complex,
+                   const int *isbloch, const double *e, const double *alpha, void *stream);
+int sgc_apply_grad(void *G, const void *f, int opmode, int dtype, int ndim, const int64_t *N,
+                   const int *isfwd, const void *const *dlinv, int coef_complex,
+                   const int *isbloch, const double *e, const double *alpha, void *stream);
+int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int ndim, const int64_t *N,
+                   const int *isfwd, const void *const *dl, const void *const *dlpinv,
+                   int coef_complex, const int *isbloch, const double *e, const double *alpha,
+                   void *stream);
+
+/* Host-array convenience (strict drop-in for Julia `Array`s; PCIe-bound): copies F (and G for
+ * SGC_OP_ADD) to the device, applies, copies G back, synchronises.  `G_host`/`F_host` hold
+ * n_out / n_in components of prod(N) elements each. */
+int sgc_op_apply_host(const sgc_op *op, void *G_host, const void *F_host, int opmode);
+
+/* ---------------------------------------------------------------------------------------- */
+/* Sparse assembly: create_* → SparseMatrixCSC{T,Int64}                                      */
+/* Two steps, so that the caller owns the output arrays (Julia Vectors or device buffers):   */
+/*   sgc_asm_create_*  describe the operator (host work O(ΣN));                               */
+/*   sgc_asm_colptr    count + prefix-scan on the device → colptr and nnz;                    */
+/*   sgc_asm_fill      write rowval / nzval (rows ascending in each column, duplicates        */
+/*                     summed, stored zeros dropped: `dropzeros!(sparse(I,J,V,m,n))`).        */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct sgc_asm sgc_asm;
+
+/* create_∂  — matrix/differential/partial.jl:45-60, create_∂info :87-314 */
+int sgc_asm_create_partial(sgc_asm **a, int ndim, const int64_t *N, int nw, int isfwd,
+                           const void *dwinv, int coef_complex, int isbloch, const double *e,
+                           int e_complex);
+/* create_m̂  — matrix/mean.jl:124-138, create_minfo :141-377 (dw == dwpinv == NULL: ones) */
+int sgc_asm_create_mhat(sgc_asm **a, int ndim, const int64_t *N, int nw, int isfwd, const void *dw,
+                        const void *dwpinv, int coef_complex, int isbloch, const double *e,
+                        int e_complex);
+/* create_curl  — matrix/differential/curl.jl:50-104 */
+int sgc_asm_create_curl(sgc_asm **a, int ndim, const int64_t *N, const int *isfwd,
+                        const void *const *dlinv, int coef_complex, const int *isbloch,
+                        const double *e, int e_complex, const int *cmp_shp, int Kout,
+                        const int *cmp_out, int Kin, const int *cmp_in, int order_cmpfirst);
+/* create_divg / create_grad  — matrix/differential/divergence.jl:37-70, gradient.jl:37-70 */
+int sgc_asm_create_divg(sgc_asm **a, int ndim, const int64_t *N, const int *isfwd,
+                        const void *const *dlinv, int coef_complex, const int *isbloch,
+                        const double *e, int e_complex, int order_cmpfirst);
+int sgc_asm_create_grad(sgc_asm **a, int ndim, const int64_t *N, const int *isfwd,
+                        const void *const *dlinv, int coef_complex, const int *isbloch,
+                        const double *e, int e_complex, int order_cmpfirst);
+/* create_mean  — matrix/mean.jl:72-111 */
+int sgc_asm_create_mean(sgc_asm **a, int ndim, const int64_t *N, const int *isfwd,
+                        const void *const *dl, const void *const *dlpinv, int coef_complex,
+                        const int *isbloch, const double *e, int e_complex, int order_cmpfirst);
+/* create_πcmp  — matrix/permutation.jl:15-40.  `scale` holds Kf Float64 or ComplexF64. */
+int sgc_asm_create_picmp(sgc_asm **a, int ndim, const int64_t *N, int Kf, const int *permute,
+                         const void *scale, int scale_complex, int order_cmpfirst);
+
+/* Row partition for multi-GPU assembly: keep only the global rows
+ * [row_begin, row_end) (0-based, half-open) and emit them re-based to the block.  The vertical
+ * concatenation of the blocks of a partition of 0..m equals the global matrix. */
+int sgc_asm_set_row_range(sgc_asm *a, int64_t row_begin, int64_t row_end);
+
+/* m, n of the (block of the) matrix and its value type (SGC_F64 / SGC_C128 =
+ * promote_type of the inputs, curl.jl:59). */
+int sgc_asm_shape(const sgc_asm *a, int64_t *m, int64_t *n, int *val_dtype);
+
+/* colptr: DEVICE pointer to n+1 Int64.  index_base 1 gives Julia's 1-based arrays, 0 gives
+ * C/scipy.  *nnz (host) is written after the scan has completed (this call synchronises). */
+int sgc_asm_colptr(sgc_asm *a, int64_t *colptr, int index_base, int64_t *nnz, void *stream);
+
+/* rowval: DEVICE pointer to nnz Int64; nzval: DEVICE pointer to nnz values of val_dtype. */
+int sgc_asm_fill(const sgc_asm *a, const int64_t *colptr, int index_base, int64_t *rowval,
+                 void *nzval, void *stream);
+
+/* Generic cross-check path (north-star wording): emit the reference's COO triplets per block
+ * on the device, radix-sort by (column,row), sum duplicates, drop zeros.  Same outputs as the
+ * two calls above; slower; used by the tests to validate the closed-form kernels. */
+int sgc_asm_coo_sort(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval,
+                     int64_t nnz_capacity, int64_t *nnz, void *stream);
+
+/* Host-array convenience: colptr/rowval/nzval are HOST pointers (call sgc_asm_nnz_host first
+ * to size rowval / nzval). */
+int sgc_asm_nnz_host(sgc_asm *a, int64_t *nnz);
+int sgc_asm_fill_host(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval);
+
+int sgc_asm_destroy(sgc_asm *a);
+
+/* y = A·x for an assembled CSC matrix on the device (the cross-check `mul!(g, Curl, f)` of
+ * test/curl.jl:55).  One thread per column, atomics on y; test utility, not a tuned SpMV. */
+int sgc_csc_matvec(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval,
+                   const void *nzval, int index_base, int val_dtype, const void *x, void *y,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGC_B200_H */

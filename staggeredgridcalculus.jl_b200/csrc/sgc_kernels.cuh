@@ -1,0 +1,394 @@
+// sgc_kernels.cuh — matrix-free stencil kernels (hand-written for sm_100a).
+//
+//   k_term      one block of an operator: Gv OP (∂w | m̂w)(Fu) for one component pair
+//               (matrixfree/differential/partial.jl:33-451, matrixfree/mean.jl:102-922).
+//   k_curl3     the fused full 3-D curl (matrixfree/differential/curl.jl:52-137): all six
+//               ∂ blocks in ONE pass, z-march with register-resident planes, y-neighbours
+//               through a shared-memory tile, x-neighbours through warp shuffles, all
+//               boundary rules (Bloch phase, PEC/PMC symmetry, slab interfaces) folded in.
+//
+// Every formula keeps the reference's operand order; the library is
+// built with -fmad=false so nothing is contracted.
+#pragma once
+#include "sgc_common.cuh"
+
+namespace sgc {
+
+enum : int { KIND_PARTIAL = 0, KIND_MEAN_ARITH = 1, KIND_MEAN_WEIGHTED = 2 };
+enum : int { BC_BLOCH = 0, BC_SYM = 1, BC_IFACE = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// Generic single-term kernel
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename C>
+struct TermParams {
+    T *G;             // output component
+    const T *F;       // input component
+    const T *ghost;   // plane replacing the wrap-around plane (never null; aliases F when local)
+    const C *c;       // ∂: α·∆w⁻¹[i]          m̂ weighted: (0.5α)·∆w′⁻¹[i]     (length Nw)
+    const C *w;       // m̂ weighted: ∆w[i]                                     (length Nw)
+    C a2, a1;         // m̂ arithmetic: 0.5α, α
+    C b0;             // m̂ weighted, backward+symmetry: α·∆w′⁻¹[1]
+    C w_hi, w_lo;     // m̂ weighted: ∆w of the ghost plane above / below
+    cplx e;           // e⁻ⁱᵏᴸ
+    int e_real;       // e is a Julia Real
+    int fwd;
+    int bc_lo, bc_hi; // BC_BLOCH | BC_SYM | BC_IFACE at i = 0 / i = Nw-1
+    int64_t inner;    // product of the dims faster than the operator axis
+    int64_t Nw;       // length of the operator axis
+    int64_t outer;    // product of the slower dims
+    int64_t i_begin, i_end;  // restriction along the operator axis   (range applies here if it is the last dim)
+    int64_t o_begin, o_end;  // restriction along the outer index
+    int64_t ghost_stride_o;  // element stride of `ghost` per outer index (0 when outer is not used)
+};
+
+template <typename T, typename C, int KIND>
+SGC_D T term_value(const TermParams<T, C> &p, int64_t x, int64_t i, int64_t o) {
+    const int64_t Nw = p.Nw;
+    const int64_t base = (o * Nw) * p.inner + x;
+    const T cur = ldg_stream(p.F + base + i * p.inner);
+    if (p.fwd) {
+        if (i == Nw - 1) {  // positive end
+            if (p.bc_hi == BC_SYM) {
+                if (KIND == KIND_PARTIAL) return neg(mul(p.c[i], cur));             // partial.jl:84-87
+                if (KIND == KIND_MEAN_ARITH) return mul(p.a2, cur);                 // mean.jl:149-151
+                return mul(mul(p.c[i], p.w[i]), cur);                               // mean.jl:546-549
+            }
+            T g = ldg_plain(p.ghost + o * p.ghost_stride_o + x);
+            if (p.bc_hi == BC_BLOCH) {
+                if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(mul_e(p.e, g, p.e_real), cur));    // :62-65
+                if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(mul_e(p.e, g, p.e_real), cur));   // :129-131
+                return mul(p.c[i], add(mul(p.w_hi, g), mul(p.w[i], cur)));  // w_hi = ∆w[1]*e      // :524-527
+            }
+            if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(g, cur));
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(g, cur));
+            return mul(p.c[i], add(mul(p.w_hi, g), mul(p.w[i], cur)));
+        }
+        const T nb = ldg_stream(p.F + base + (i + 1) * p.inner);
+        if (i == 0 && p.bc_lo == BC_SYM) {  // negative end, input forced to zero
+            if (KIND == KIND_PARTIAL) return mul(p.c[0], nb);                        // partial.jl:77-80
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a2, nb);                       // mean.jl:143-145
+            return mul(mul(p.c[0], p.w[1]), nb);                                     // mean.jl:539-542
+        }
+        if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(nb, cur));                  // partial.jl:54-58
+        if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(nb, cur));                 // mean.jl:121-125
+        return mul(p.c[i], add(mul(p.w[i + 1], nb), mul(p.w[i], cur)));              // mean.jl:516-520
+    }
+    // backward
+    if (i == 0) {
+        if (p.bc_lo == BC_SYM) {
+            if (KIND == KIND_PARTIAL) return zero_of(cur);                           // partial.jl:184-188
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a1, cur);                      // mean.jl:241-245
+            return mul(mul(p.b0, p.w[0]), cur);                                      // mean.jl:646-650
+        }
+        T g = ldg_plain(p.ghost + o * p.ghost_stride_o + x);
+        if (p.bc_lo == BC_BLOCH) {
+            if (KIND == KIND_PARTIAL) return mul(p.c[0], sub(cur, div_e(g, p.e, p.e_real)));       // :179-183
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, div_e(g, p.e, p.e_real)));      // :237-240
+            return mul(p.c[0], add(mul(p.w[0], cur), div_e(mul(p.w_lo, g), p.e, p.e_real)));       // :641-645
+        }
+        if (KIND == KIND_PARTIAL) return mul(p.c[0], sub(cur, g));
+        if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, g));
+        return mul(p.c[0], add(mul(p.w[0], cur), mul(p.w_lo, g)));
+    }
+    const T nb = ldg_stream(p.F + base + (i - 1) * p.inner);
+    if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(cur, nb));                      // partial.jl:171-175
+    if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, nb));                     // mean.jl:229-233
+    return mul(p.c[i], add(mul(p.w[i], cur), mul(p.w[i - 1], nb)));                  // mean.jl:633-637
+}
+
+// Thread mapping.  The three logical indices are x (fastest, `inner` long), i (operator axis)
+// and o (outer).  XAXIS = true is the case inner == 1 (operator along the contiguous axis):
+// threadIdx.x runs along i and (blockIdx.y, threadIdx.y) along o.  Otherwise threadIdx.x runs
+// along x, (blockIdx.y, threadIdx.y) along i and blockIdx.z along o.
+template <typename T, typename C, int KIND, bool ADD, bool XAXIS>
+__global__ void __launch_bounds__(256) k_term(const __grid_constant__ TermParams<T, C> p) {
+    if (XAXIS) {
+        const int64_t i = p.i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= p.i_end) return;
+        for (int64_t o = p.o_begin + (int64_t)blockIdx.y * blockDim.y + threadIdx.y; o < p.o_end;
+             o += (int64_t)gridDim.y * blockDim.y) {
+            T v = term_value<T, C, KIND>(p, 0, i, o);
+            T *g = p.G + o * p.Nw + i;
+            if (ADD) v = add(ldg_plain(g), v);
+            stg_stream(g, v);
+        }
+    } else {
+        const int64_t x = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (x >= p.inner) return;
+        for (int64_t o = p.o_begin + blockIdx.z; o < p.o_end; o += gridDim.z) {
+            for (int64_t i = p.i_begin + (int64_t)blockIdx.y * blockDim.y + threadIdx.y; i < p.i_end;
+                 i += (int64_t)gridDim.y * blockDim.y) {
+                T v = term_value<T, C, KIND>(p, x, i, o);
+                T *g = p.G + (o * p.Nw + i) * p.inner + x;
+                if (ADD) v = add(ldg_plain(g), v);
+                stg_stream(g, v);
+            }
+        }
+    }
+}
+
+// Gv .= 0   (matrixfree/differential/curl.jl:77) restricted to a contiguous range
+template <typename T>
+__global__ void __launch_bounds__(256) k_fill_zero(T *G, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n;
+         q += (int64_t)gridDim.x * blockDim.x)
+        stg_stream(G + q, zero_of(T{}));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused full 3-D curl
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename C>
+struct CurlParams {
+    const T *F[3];       // Fx, Fy, Fz  (each Nx*Ny*Nz)
+    T *G[3];             // Gx, Gy, Gz
+    const T *ghost[2];   // z-ghost planes of Fx, Fy (Nx*Ny each); alias F's own wrap plane when local
+    const C *c[3];       // α·∆x⁻¹[i], α·∆y⁻¹[j], α·∆z⁻¹[k]
+    cplx e[3];
+    int e_real[3];
+    int fwd[3];
+    int bc_lo[3], bc_hi[3];
+    int Nx, Ny, Nz;
+    int k_begin, k_end;  // planes to produce
+    int march;           // planes per CTA
+};
+
+// One CTA owns a TX×TY column of cells and marches `march` planes up in z.
+//   * Fx, Fy: two planes live in registers (`lo`, `hi`); ∂z = cz[k]·(hi − lo) for both forward
+//     (lo = plane k, hi = k+1) and backward (lo = k−1, hi = k) differences, so every plane
+//     of Fx, Fy is loaded from HBM exactly once per CTA (+1 at the start of the march).
+//   * y-neighbours of Fx and Fz come from a (TY+1)×TX shared-memory tile (double-buffered,
+//     one __syncthreads per plane); the extra row is the only y-halo traffic.
+//   * x-neighbours of Fy and Fz come from the neighbouring lane (__shfl); the lane at the edge
+//     of the warp loads the single missing element itself.
+//   * loads for plane k+1 are issued before plane k is computed (register prefetch).
+template <typename T, typename C, bool ADD, int TX, int TY>
+__global__ void __launch_bounds__(TX *TY, (TX * TY <= 256) ? 2 : 1) k_curl3(const __grid_constant__ CurlParams<T, C> p) {
+    static_assert(TX % 32 == 0, "a warp must lie inside one row");
+    __shared__ T sFx[2][TY + 1][TX];
+    __shared__ T sFz[2][TY + 1][TX];
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int lane = tx & 31;
+    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz;
+    const int i = blockIdx.x * TX + tx;
+    const int j = blockIdx.y * TY + ty;
+    const bool valid = (i < Nx) && (j < Ny);
+    const int64_t sy = Nx, sz = (int64_t)Nx * Ny;
+    const int64_t ij = (int64_t)j * sy + i;
+
+    const int fx = p.fwd[0], fy = p.fwd[1], fz = p.fwd[2];
+
+    // ---- per-thread x-edge description (who supplies the x-neighbour) ------------------------
+    // forward: neighbour is i+1, taken from lane+1; backward: i-1 from lane-1.
+    // xload: this lane must fetch its neighbour from memory at index xnb (warp edge or wrap).
+    // xkind: 0 plain neighbour, 1 Bloch wrap (apply e), 2 symmetric ghost / zero term.
+    int xnb, xkind = 0;
+    bool xload;
+    if (fx) {
+        const bool last = (i == Nx - 1);
+        xnb = last ? 0 : i + 1;
+        xkind = last ? (p.bc_hi[0] == BC_BLOCH ? 1 : 2) : 0;
+        xload = valid && (last ? (xkind == 1) : (lane == 31));
+    } else {
+        const bool first = (i == 0);
+        xnb = first ? Nx - 1 : i - 1;
+        xkind = first ? (p.bc_lo[0] == BC_BLOCH ? 1 : 2) : 0;
+        xload = valid && (first ? (xkind == 1) : (lane == 0));
+    }
+    const bool x_lo_zero = fx && (i == 0) && (p.bc_lo[0] == BC_SYM);  // forward symmetric: Fu[1] := 0
+    const int64_t xnb_off = (int64_t)j * sy + xnb;
+
+    // ---- per-thread y-edge description ------------------------------------------------------------
+    int ykind = 0;  // 0 plain, 1 Bloch wrap, 2 symmetric
+    if (fy) {
+        if (j == Ny - 1) ykind = (p.bc_hi[1] == BC_BLOCH) ? 1 : 2;
+    } else {
+        if (j == 0) ykind = (p.bc_lo[1] == BC_BLOCH) ? 1 : 2;
+    }
+    const bool y_lo_zero = fy && (j == 0) && (p.bc_lo[1] == BC_SYM);
+    // row of the shared tile holding this thread's y-neighbour: tile row r holds grid row
+    // j0 + r (forward, halo = row TY) or j0 - 1 + r (backward, halo = row 0).
+    const int srow_self = fy ? ty : ty + 1;
+    const int srow_nb = fy ? ty + 1 : ty;
+    // halo row loader: the first TX*2 threads (linear id) fetch the halo row of Fx and Fz.
+    const int lin = ty * TX + tx;
+    const bool is_halo_loader = lin < 2 * TX;
+    const int hcomp = lin / TX;  // 0 → Fx, 1 → Fz
+    const int hx = lin % TX;
+    const int hi_ = blockIdx.x * TX + hx;
+    int hj;  // grid row of the halo
+    bool hload = false;
+    if (is_halo_loader && hi_ < Nx) {
+        if (fy) {
+            hj = blockIdx.y * TY + TY;  // may exceed the last row when the tile is ragged
+            const int jlast = min(blockIdx.y * TY + TY, Ny) - 1;  // last valid row of this tile
+            hj = jlast + 1;
+            if (hj >= Ny) { hj = 0; hload = (p.bc_hi[1] == BC_BLOCH); }
+            else hload = true;
+        } else {
+            hj = blockIdx.y * TY - 1;
+            if (hj < 0) { hj = Ny - 1; hload = (p.bc_lo[1] == BC_BLOCH); }
+            else hload = true;
+        }
+    }
+    // In a ragged forward tile the halo row sits right after the last valid row.
+    const int hrow = fy ? (min(blockIdx.y * TY + TY, Ny) - blockIdx.y * TY) : 0;
+    const int64_t h_off = hload ? ((int64_t)hj * sy + hi_) : 0;
+    const T *hsrc = (hcomp == 0) ? p.F[0] : p.F[2];
+
+    const C cxi = valid ? p.c[0][i] : C{};
+    const C cyj = valid ? p.c[1][j] : C{};
+
+    const int k0 = p.k_begin + blockIdx.z * p.march;
+    const int k1 = min(k0 + p.march, p.k_end);
+    if (k0 >= k1) return;
+
+    const T Z = zero_of(T{});
+
+    // plane fetch helpers -----------------------------------------------------------------------
+    // "hi" plane index for output plane k: forward k+1, backward k.   "lo": forward k, backward k-1.
+    // Out-of-range hi/lo planes come from the ghost pointers (wrap plane or neighbour rank).
+    auto load_xy_plane = [&](int comp, int kp) -> T {  // comp 0/1 = Fx/Fy, raw value of plane kp
+        if (!valid) return Z;
+        if (kp < 0 || kp >= Nz) return ldg_plain(p.ghost[comp] + ij);
+        return ldg_stream(p.F[comp] + (int64_t)kp * sz + ij);
+    };
+
+    // prologue: lo planes of Fx, Fy for k0
+    T xlo = load_xy_plane(0, fz ? k0 : k0 - 1);
+    T ylo = load_xy_plane(1, fz ? k0 : k0 - 1);
+    // prefetch registers for plane k0
+    T xhi_n = load_xy_plane(0, fz ? k0 + 1 : k0);
+    T yhi_n = load_xy_plane(1, fz ? k0 + 1 : k0);
+    T zc_n = valid ? ldg_stream(p.F[2] + (int64_t)k0 * sz + ij) : Z;
+    T yx_n = Z, zx_n = Z;   // x-edge elements of Fy, Fz (centre plane)
+    T h_n = Z;              // halo-row element (Fx or Fz, centre plane)
+    {
+        const int kc = k0;  // centre plane
+        if (xload) {
+            // Fy centre plane: forward-z centre is plane k (== lo), backward-z centre is plane k (== hi)
+            yx_n = ldg_stream(p.F[1] + (int64_t)kc * sz + xnb_off);
+            zx_n = ldg_stream(p.F[2] + (int64_t)kc * sz + xnb_off);
+        }
+        if (hload) h_n = ldg_stream(hsrc + (int64_t)kc * sz + h_off);
+    }
+
+    int buf = 0;
+    for (int k = k0; k < k1; ++k, buf ^= 1) {
+        const T xhi = xhi_n, yhi = yhi_n, zc = zc_n, yxe = yx_n, zxe = zx_n, he = h_n;
+        // ---- issue the loads of plane k+1 ------------------------------------------------------
+        if (k + 1 < k1) {
+            xhi_n = load_xy_plane(0, fz ? k + 2 : k + 1);
+            yhi_n = load_xy_plane(1, fz ? k + 2 : k + 1);
+            zc_n = valid ? ldg_stream(p.F[2] + (int64_t)(k + 1) * sz + ij) : Z;
+            if (xload) {
+                yx_n = ldg_stream(p.F[1] + (int64_t)(k + 1) * sz + xnb_off);
+                zx_n = ldg_stream(p.F[2] + (int64_t)(k + 1) * sz + xnb_off);
+            }
+            if (hload) h_n = ldg_stream(hsrc + (int64_t)(k + 1) * sz + h_off);
+        }
+        // centre-plane values of Fx, Fy
+        const T xc = fz ? xlo : xhi;
+        const T yc = fz ? ylo : yhi;
+
+        // ---- publish Fx, Fz centre values for the y-neighbour exchange ---------------------------
+        if (valid) {  // rows beyond the grid stay unwritten: the halo row may live there
+            sFx[buf][srow_self][tx] = xc;
+            sFz[buf][srow_self][tx] = zc;
+        }
+        if (is_halo_loader) {
+            if (hcomp == 0) sFx[buf][hrow][hx] = he;
+            else sFz[buf][hrow][hx] = he;
+        }
+        __syncthreads();
+
+        // ---- z terms:  cz[k]·(hi − lo) with boundary rules ----------------------------------------
+        const C czk = p.c[2][k];
+        T dzx, dzy;  // ∂z Fx, ∂z Fy (already multiplied by α·∆z⁻¹[k])
+        {
+            T xh = xhi, yh = yhi, xl = xlo, yl = ylo;
+            bool zero_term = false;
+            if (fz) {
+                if (k == Nz - 1) {
+                    if (p.bc_hi[2] == BC_BLOCH) { xh = mul_e(p.e[2], xh, p.e_real[2]); yh = mul_e(p.e[2], yh, p.e_real[2]); }
+                    else if (p.bc_hi[2] == BC_SYM) { xh = Z; yh = Z; }
+                }
+                if (k == 0 && p.bc_lo[2] == BC_SYM) { xl = Z; yl = Z; }
+            } else if (k == 0) {
+                if (p.bc_lo[2] == BC_BLOCH) { xl = div_e(xl, p.e[2], p.e_real[2]); yl = div_e(yl, p.e[2], p.e_real[2]); }
+                else if (p.bc_lo[2] == BC_SYM) zero_term = true;
+            }
+            dzx = zero_term ? Z : mul(czk, sub(xh, xl));
+            dzy = zero_term ? Z : mul(czk, sub(yh, yl));
+        }
+
+        // ---- y terms: neighbours from shared memory ------------------------------------------------
+        T dyx, dyz;  // ∂y Fx, ∂y Fz
+        {
+            T xn = sFx[buf][srow_nb][tx];
+            T zn = sFz[buf][srow_nb][tx];
+            T xh, xl, zh, zl;
+            bool zero_term = false;
+            if (fy) {
+                xh = xn; zh = zn; xl = xc; zl = zc;
+                if (ykind == 1) { xh = mul_e(p.e[1], xh, p.e_real[1]); zh = mul_e(p.e[1], zh, p.e_real[1]); }
+                else if (ykind == 2) { xh = Z; zh = Z; }
+                if (y_lo_zero) { xl = Z; zl = Z; }
+            } else {
+                xh = xc; zh = zc; xl = xn; zl = zn;
+                if (ykind == 1) { xl = div_e(xl, p.e[1], p.e_real[1]); zl = div_e(zl, p.e[1], p.e_real[1]); }
+                else if (ykind == 2) zero_term = true;
+            }
+            dyx = zero_term ? Z : mul(cyj, sub(xh, xl));
+            dyz = zero_term ? Z : mul(cyj, sub(zh, zl));
+        }
+
+        // ---- x terms: neighbours from the adjacent lane --------------------------------------------
+        T dxy, dxz;  // ∂x Fy, ∂x Fz
+        {
+            T yn = fx ? shfl_down1(yc) : shfl_up1(yc);
+            T zn = fx ? shfl_down1(zc) : shfl_up1(zc);
+            if (xload) { yn = yxe; zn = zxe; }
+            T yh, yl, zh, zl;
+            bool zero_term = false;
+            if (fx) {
+                yh = yn; zh = zn; yl = yc; zl = zc;
+                if (xkind == 1) { yh = mul_e(p.e[0], yh, p.e_real[0]); zh = mul_e(p.e[0], zh, p.e_real[0]); }
+                else if (xkind == 2) { yh = Z; zh = Z; }
+                if (x_lo_zero) { yl = Z; zl = Z; }
+            } else {
+                yh = yc; zh = zc; yl = yn; zl = zn;
+                if (xkind == 1) { yl = div_e(yl, p.e[0], p.e_real[0]); zl = div_e(zl, p.e[0], p.e_real[0]); }
+                else if (xkind == 2) zero_term = true;
+            }
+            dxy = zero_term ? Z : mul(cxi, sub(yh, yl));
+            dxz = zero_term ? Z : mul(cxi, sub(zh, zl));
+        }
+
+        // ---- combine in the reference's accumulation order (curl.jl:66-91) ------------------------
+        //   Gx: −∂zFy then +∂yFz ;  Gy: +∂zFx then −∂xFz ;  Gz: −∂yFx then +∂xFy
+        if (valid) {
+            const int64_t o = (int64_t)k * sz + ij;
+            T gx, gy, gz;
+            if (ADD) {
+                gx = add(add(ldg_plain(p.G[0] + o), neg(dzy)), dyz);
+                gy = add(add(ldg_plain(p.G[1] + o), dzx), neg(dxz));
+                gz = add(add(ldg_plain(p.G[2] + o), neg(dyx)), dxy);
+            } else {
+                gx = add(add(Z, neg(dzy)), dyz);  // Gv .= 0 ; += (−∂zFy) ; += ∂yFz
+                gy = add(dzx, neg(dxz));
+                gz = add(neg(dyx), dxy);
+            }
+            stg_stream(p.G[0] + o, gx);
+            stg_stream(p.G[1] + o, gy);
+            stg_stream(p.G[2] + o, gz);
+        }
+        // rotate planes
+        xlo = xhi;
+        ylo = yhi;
+    }
+}
+
+}  // namespace sgc

@@ -1,0 +1,394 @@
+"""GPU parity tests of the matrix-free operators: CUDA library (through the C ABI) vs oracle.
+
+Same seeded inputs on both sides; sizes chosen so that the numpy oracle finishes in seconds.
+The expected agreement is bit-for-bit (identical IEEE operations in identical order); the
+north-star tolerance (4 ulp / 1e-13) is the hard limit, `exact=True` marks the cases where
+bit equality is additionally REQUIRED.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import sgc_oracle as O
+from tests.util import assert_parity, rand_field, rand_coef
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sgc_b200
+    return sgc_b200
+
+
+def dev(S, a):
+    return S.DeviceArray.from_numpy(a)
+
+
+# ------------------------------------------------------------------------------------------------
+# apply_∂!
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [(10,), (8, 9), (8, 9, 10), (33, 5, 3), (1, 4, 2), (70, 1, 1)])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_apply_partial_matches_oracle(S, N, cplx):
+    """test/partial.jl:67-70 widened: every axis, fwd/bwd, Bloch/symmetric, '=' and '+='."""
+    rng = np.random.default_rng(100 + len(N) + 7 * cplx)
+    Fu = rand_field(rng, N, cplx)
+    G0 = rand_field(rng, N, cplx)
+    for nw in range(1, len(N) + 1):
+        for isfwd, isbloch, op in itertools.product((True, False), (True, False), ("=", "+=")):
+            if isfwd and not isbloch and N[nw - 1] < 2:
+                continue
+            dwinv = rand_coef(rng, N[nw - 1], False)
+            Gref = G0.copy(order="F")
+            O.apply_partial(Gref, Fu, op, nw, isfwd, dwinv, isbloch)
+            Gd = dev(S, G0)
+            S.apply_partial(Gd, dev(S, Fu), op, nw, isfwd, dwinv, isbloch)
+            assert_parity(Gd.numpy(), Gref, f"∂ N={N} nw={nw} fwd={isfwd} bloch={isbloch} {op}", exact=True)
+
+
+@pytest.mark.parametrize("N", [(9,), (6, 7), (5, 6, 7)])
+def test_apply_partial_complex_everything(S, N):
+    """PML-stretched (complex) ∆w⁻¹, complex Bloch phase, complex α, scalar ∆ wrapper."""
+    rng = np.random.default_rng(7)
+    Fu = rand_field(rng, N, True)
+    G0 = rand_field(rng, N, True)
+    for nw in range(1, len(N) + 1):
+        for isfwd, isbloch, op in itertools.product((True, False), (True, False), ("=", "+=")):
+            for dwinv, e, alpha in [(rand_coef(rng, N[nw - 1], True), np.exp(-0.7j), 1.0),
+                                    (rand_coef(rng, N[nw - 1], False), np.exp(0.3j), 0.5 - 0.25j),
+                                    (rand_coef(rng, N[nw - 1], True), -1.0, 2.0),
+                                    (0.75, np.exp(-1.1j), -1.5)]:
+                Gref = G0.copy(order="F")
+                O.apply_partial(Gref, Fu, op, nw, isfwd, dwinv, isbloch, e, alpha=alpha)
+                Gd = dev(S, G0)
+                S.apply_partial(Gd, dev(S, Fu), op, nw, isfwd, dwinv, isbloch, e, alpha=alpha)
+                assert_parity(Gd.numpy(), Gref, f"∂ complex N={N} nw={nw} fwd={isfwd} bloch={isbloch} {op}")
+
+
+def test_apply_partial_errors(S):
+    Fu = dev(S, np.zeros((4, 5)))
+    with pytest.raises(S.SgcError):  # @assert size(Gv)==size(Fu)          partial.jl:251
+        S.apply_partial(dev(S, np.zeros((4, 6))), Fu, "=", 1, True)
+    with pytest.raises(S.SgcError):  # @assert 1≤nw≤K
+        S.apply_partial(dev(S, np.zeros((4, 5))), Fu, "=", 3, True)
+    with pytest.raises(S.SgcError):  # @assert size(Fu,nw)==length(∆w⁻¹)   partial.jl:253
+        S.apply_partial(dev(S, np.zeros((4, 5))), Fu, "=", 1, True, np.ones(5))
+    with pytest.raises(S.InexactError):  # complex value into a Float64 array
+        S.apply_partial(dev(S, np.zeros((4, 5))), Fu, "=", 1, True, 1.0, True, np.exp(1j))
+    with pytest.raises(S.SgcError):  # forward symmetric needs Fu[2]
+        S.apply_partial(dev(S, np.zeros((1, 5))), dev(S, np.zeros((1, 5))), "=", 1, True, 1.0, False)
+
+
+# ------------------------------------------------------------------------------------------------
+# apply_m̂!, apply_mean!
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [(10,), (8, 9), (3, 4, 5), (34, 3, 2)])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_apply_mhat_matches_oracle(S, N, cplx):
+    """test/mean.jl:86-89 widened to the arithmetic variant, complex data and '+='."""
+    rng = np.random.default_rng(200 + len(N))
+    Fu = rand_field(rng, N, cplx)
+    G0 = rand_field(rng, N, cplx)
+    for nw in range(1, len(N) + 1):
+        for isfwd, isbloch, op, weighted in itertools.product((True, False), (True, False), ("=", "+="), (False, True)):
+            if isfwd and not isbloch and N[nw - 1] < 2:
+                continue
+            dw = rand_coef(rng, N[nw - 1], False) if weighted else None
+            dwp = rand_coef(rng, N[nw - 1], cplx) if weighted else None
+            e = np.exp(-0.4j) if cplx else -1.0
+            alpha = (0.5 + 0.5j) if cplx else 1.25
+            Gref = G0.copy(order="F")
+            O.apply_mhat(Gref, Fu, op, nw, isfwd, dw, dwp, isbloch, e, alpha=alpha)
+            Gd = dev(S, G0)
+            S.apply_mhat(Gd, dev(S, Fu), op, nw, isfwd, dw, dwp, isbloch, e, alpha=alpha)
+            assert_parity(Gd.numpy(), Gref, f"m̂ N={N} nw={nw} fwd={isfwd} bloch={isbloch} {op} w={weighted}")
+
+
+@pytest.mark.parametrize("N", [(10,), (8, 9), (3, 4, 5)])
+def test_apply_mean_matches_oracle(S, N):
+    """test/mean.jl:100-102."""
+    rng = np.random.default_rng(300)
+    K = len(N)
+    F = rand_field(rng, N + (K,), True)
+    G0 = rand_field(rng, N + (K,), True)
+    for isfwd, isbloch, op, weighted in itertools.product((True, False), (True, False), ("=", "+="), (False, True)):
+        dl = [rand_coef(rng, n, False) for n in N] if weighted else None
+        dlp = [rand_coef(rng, n, False) for n in N] if weighted else None
+        e = [np.exp(-0.2j * (k + 1)) for k in range(K)]
+        Gref = G0.copy(order="F")
+        O.apply_mean(Gref, F, op, [isfwd] * K, dl, dlp, [isbloch] * K, e)
+        Gd = dev(S, G0)
+        S.apply_mean(Gd, dev(S, F), op, [isfwd] * K, dl, dlp, [isbloch] * K, e)
+        assert_parity(Gd.numpy(), Gref, f"mean N={N} fwd={isfwd} bloch={isbloch} {op} w={weighted}")
+
+
+# ------------------------------------------------------------------------------------------------
+# apply_curl!  (fused kernel for the full 3-D curl)
+# ------------------------------------------------------------------------------------------------
+CURL_SIZES = [(3, 4, 5), (37, 19, 11), (64, 16, 9), (5, 3, 2), (33, 9, 1), (1, 1, 4), (2, 2, 2)]
+
+
+@pytest.mark.parametrize("N", CURL_SIZES)
+@pytest.mark.parametrize("isfwd", list(itertools.product((False, True), repeat=3)))
+def test_apply_curl_matches_oracle(S, N, isfwd):
+    """test/curl.jl:54-57: nonuniform ∆l⁻¹, isbloch = [T,F,F], random complex Bloch phases;
+    plus all-Bloch and all-symmetric, '=' and '+='."""
+    rng = np.random.default_rng(400 + sum(N))
+    F = rand_field(rng, N + (3,), True)
+    G0 = rand_field(rng, N + (3,), True)
+    dlinv = [rand_coef(rng, n, False) for n in N]
+    e = rng.uniform(-1, 1, 3) + 1j * rng.uniform(-1, 1, 3)
+    for isbloch in ([True, False, False], [True, True, True], [False, False, False], [False, True, True]):
+        if any(f and not b and n < 2 for f, b, n in zip(isfwd, isbloch, N)):
+            continue
+        for op in ("=", "+="):
+            Gref = G0.copy(order="F")
+            O.apply_curl(Gref, F, op, isfwd, dlinv, isbloch, e)
+            Gd = dev(S, G0)
+            S.apply_curl(Gd, dev(S, F), op, isfwd, dlinv, isbloch, e)
+            assert_parity(Gd.numpy(), Gref, f"curl N={N} fwd={isfwd} bloch={isbloch} {op}", exact=True)
+
+
+@pytest.mark.parametrize("cplx_field,cplx_coef,alpha", [(False, False, 1.0), (False, False, -2.5),
+                                                        (True, True, 1.0), (True, False, 0.3 - 0.8j),
+                                                        (True, True, 1.5 + 0.5j)])
+def test_apply_curl_dtypes_and_alpha(S, cplx_field, cplx_coef, alpha):
+    """Float64 fields, PML-stretched complex ∆l⁻¹, α ≠ 1 (gaps listed in SURVEY.md §4)."""
+    rng = np.random.default_rng(500)
+    N = (21, 10, 7)
+    F = rand_field(rng, N + (3,), cplx_field)
+    G0 = rand_field(rng, N + (3,), cplx_field)
+    dlinv = [rand_coef(rng, n, cplx_coef) for n in N]
+    e = [np.exp(-0.1j), np.exp(-0.2j), np.exp(-0.3j)] if cplx_field else [1.0, -1.0, 1.0]
+    for isfwd in ([True, True, True], [False, False, False], [True, False, True]):
+        for isbloch in ([True, True, True], [False, True, False]):
+            for op in ("=", "+="):
+                Gref = G0.copy(order="F")
+                O.apply_curl(Gref, F, op, isfwd, dlinv, isbloch, e, alpha=alpha)
+                Gd = dev(S, G0)
+                S.apply_curl(Gd, dev(S, F), op, isfwd, dlinv, isbloch, e, alpha=alpha)
+                assert_parity(Gd.numpy(), Gref, f"curl dtypes fwd={isfwd} bloch={isbloch} {op}")
+
+
+@pytest.mark.parametrize("tile", [(32, 4), (32, 8), (32, 16), (64, 4), (64, 8)])
+@pytest.mark.parametrize("march", [1, 3, 64])
+def test_fused_curl_tilings_agree_with_unfused_sweeps(S, tile, march):
+    """Every tiling / z-march length of the fused kernel gives the bits of the per-block sweeps
+    (variant 2 = the reference's own six-sweep structure on the GPU)."""
+    rng = np.random.default_rng(600)
+    N = (70, 21, 13)
+    F = dev(S, rand_field(rng, N + (3,), True))
+    G0 = rand_field(rng, N + (3,), True)
+    dlinv = [rand_coef(rng, n, True) for n in N]
+    e = [np.exp(-0.5j), np.exp(0.25j), np.exp(-1.0j)]
+    for isfwd, isbloch in [([True, True, True], [True, True, True]), ([False, False, False], [True, True, True]),
+                           ([True, False, True], [False, True, False]), ([False, True, False], [False, False, True])]:
+        for op in ("=", "+="):
+            o = S.Operator.curl(S.SGC_C128, N, isfwd, dlinv, isbloch, e, alpha=0.75)
+            Ga, Gb = dev(S, G0), dev(S, G0)
+            o.set_tuning(tile[0], tile[1], march, 0)
+            o.apply(Ga, F, op)
+            o.set_tuning(0, 0, 0, 2)
+            o.apply(Gb, F, op)
+            assert o.launches(op) == (7 if op == "=" else 6)
+            assert_parity(Ga.numpy(), Gb.numpy(), f"fused {tile} march={march} fwd={isfwd} {op}", exact=True)
+            o.destroy()
+
+
+def test_apply_subcurls_match_oracle(S):
+    """test/curl.jl:62-119: 1×1 curls in 1-D, 1×2 / 2×1 (TE/TM) curls in 2-D."""
+    rng = np.random.default_rng(700)
+    N = (3, 4, 5)
+    for isfwd in itertools.product((False, True), repeat=3):
+        dlinv = [rand_coef(rng, n, False) for n in N]
+        isbloch = [True, False, False]
+        e = rng.uniform(-1, 1, 3) + 1j * rng.uniform(-1, 1, 3)
+        for cmp_shp in ([1], [2], [3], [1, 2], [2, 3], [3, 1]):
+            if len(cmp_shp) == 1:
+                cmp_outs = [[c] for c in (1, 2, 3) if c != cmp_shp[0]]
+            else:
+                cmp_outs = [cmp_shp, [c for c in (1, 2, 3) if c not in cmp_shp]]
+            for cmp_out in cmp_outs:
+                cmp_in = [6 - cmp_shp[0] - cmp_out[0]] if len(cmp_shp) == 1 else [c for c in (1, 2, 3) if c not in cmp_out]
+                Nc = tuple(N[c - 1] for c in cmp_shp)
+                sel = lambda v: [v[c - 1] for c in cmp_shp]
+                Fc = rand_field(rng, Nc + (len(cmp_in),), True)
+                Gref = np.zeros(Nc + (len(cmp_out),), dtype=complex, order="F")
+                O.apply_curl(Gref, Fc, "=", sel(isfwd), sel(dlinv), sel(isbloch), sel(e), cmp_shp=cmp_shp,
+                             cmp_out=cmp_out, cmp_in=cmp_in)
+                Gd = dev(S, rand_field(rng, Nc + (len(cmp_out),), True))
+                S.apply_curl(Gd, dev(S, Fc), "=", sel(isfwd), sel(dlinv), sel(isbloch), sel(e), cmp_shp=cmp_shp,
+                             cmp_out=cmp_out, cmp_in=cmp_in)
+                assert_parity(Gd.numpy(), Gref, f"subcurl shp={cmp_shp} out={cmp_out} in={cmp_in}", exact=True)
+    with pytest.raises(S.SgcError):  # curl.jl:85: cmp_shp lacks the needed axis
+        S.apply_curl(dev(S, np.zeros((3, 4, 1), complex)), dev(S, np.zeros((3, 4, 1), complex)), "=", [True, True],
+                     cmp_shp=[1, 1], cmp_out=[3], cmp_in=[1])
+
+
+# ------------------------------------------------------------------------------------------------
+# apply_divg!, apply_grad!
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [(7,), (4, 5), (6, 5, 4)])
+def test_apply_divg_grad_match_oracle(S, N):
+    """test/divergence.jl:48-56, test/gradient.jl:48-56."""
+    rng = np.random.default_rng(800)
+    K = len(N)
+    F = rand_field(rng, N + (K,), True)
+    f = rand_field(rng, N, True)
+    g0 = rand_field(rng, N, True)
+    G0 = rand_field(rng, N + (K,), True)
+    for isfwd in itertools.product((False, True), repeat=K):
+        dlinv = [rand_coef(rng, n, False) for n in N]
+        isbloch = [True] + [False] * (K - 1)
+        e = rng.uniform(-1, 1, K) + 1j * rng.uniform(-1, 1, K)
+        for op in ("=", "+="):
+            gref = g0.copy(order="F")
+            O.apply_divg(gref, F, op, isfwd, dlinv, isbloch, e, alpha=0.5)
+            gd = dev(S, g0)
+            S.apply_divg(gd, dev(S, F), op, isfwd, dlinv, isbloch, e, alpha=0.5)
+            assert_parity(gd.numpy(), gref, f"divg N={N} fwd={isfwd} {op}", exact=True)
+            Gref = G0.copy(order="F")
+            O.apply_grad(Gref, f, op, isfwd, dlinv, isbloch, e, alpha=-1.0)
+            Gd = dev(S, G0)
+            S.apply_grad(Gd, dev(S, f), op, isfwd, dlinv, isbloch, e, alpha=-1.0)
+            assert_parity(Gd.numpy(), Gref, f"grad N={N} fwd={isfwd} {op}", exact=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# z-slab mode on one GPU: two slabs with ghost planes reproduce the undivided result
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("isfwd_z,isbloch_z", [(True, True), (False, True), (True, False), (False, False)])
+def test_slab_split_with_ghost_planes_equals_whole(S, isfwd_z, isbloch_z):
+    rng = np.random.default_rng(900)
+    N = (19, 11, 12)
+    ks = 5  # slab 0: planes 0..4, slab 1: planes 5..11
+    F = rand_field(rng, N + (3,), True)
+    G0 = rand_field(rng, N + (3,), True)
+    dlinv = [rand_coef(rng, n, True) for n in N]
+    isfwd = [True, False, isfwd_z]
+    isbloch = [True, False, isbloch_z]
+    e = [np.exp(-0.3j), 1.0, np.exp(0.9j)]
+    whole = S.Operator.curl(S.SGC_C128, N, isfwd, dlinv, isbloch, e)
+    Gw = dev(S, G0)
+    whole.apply(Gw, dev(S, F), "+=")
+    ref = Gw.numpy()
+    out = np.empty_like(ref)
+    slabs = [(0, ks), (ks, N[2])]
+    Fd = [dev(S, np.asfortranarray(F[:, :, a:b, :])) for a, b in slabs]
+    plane = N[0] * N[1] * 16
+    for r, (a, b) in enumerate(slabs):
+        Nl = (N[0], N[1], b - a)
+        o = S.Operator.curl(S.SGC_C128, Nl, isfwd, [dlinv[0], dlinv[1], dlinv[2][a:b]], isbloch, e)
+        o.set_slab(lo_interface=(r == 1), hi_interface=(r == 0))
+        other = Fd[1 - r]
+        No = slabs[1 - r][1] - slabs[1 - r][0]
+        ghost = []
+        for c in range(2):  # Fx, Fy need the z-neighbour plane
+            comp = other.component(c + 1)
+            # forward: plane above my top = first plane of the other slab (rank 0) or the wrap plane 0
+            # of the global grid (rank 1); backward: plane below my bottom = last plane of the other slab
+            kplane = 0 if isfwd_z else No - 1
+            ghost.append(comp.ptr + kplane * plane)
+        ghost.append(None)
+        Gd = dev(S, np.asfortranarray(G0[:, :, a:b, :]))
+        # interior planes and the boundary plane in two launches, as the overlapped halo path does
+        kb = (b - a - 1) if isfwd_z else 0
+        for k0, k1 in ((0, kb), (kb, kb + 1), (kb + 1, b - a)):
+            o.apply_range(Gd, Fd[r], "+=", k0, k1, ghost)
+        out[:, :, a:b, :] = Gd.numpy()
+        o.destroy()
+    assert_parity(out, ref, f"slab split fwd_z={isfwd_z} bloch_z={isbloch_z}", exact=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# the other boundary forms: one-shot C entry points and host arrays
+# ------------------------------------------------------------------------------------------------
+def test_one_shot_c_entry_points_and_host_arrays(S):
+    import ctypes as C
+    from sgc_b200 import _lib
+    from sgc_b200.device import coef_vectors, ints, int64s, scalar2, scalars2, stream_handle
+    rng = np.random.default_rng(1000)
+    N = (9, 8, 7)
+    F = rand_field(rng, N + (3,), True)
+    dlinv = [rand_coef(rng, n, False) for n in N]
+    isfwd, isbloch, e = [True, False, True], [True, True, False], [np.exp(-0.3j), np.exp(0.2j), 1.0]
+    Gref = np.zeros_like(F)
+    O.apply_curl(Gref, F, "=", isfwd, dlinv, isbloch, e)
+    arr, keep, cc = coef_vectors(dlinv, N)
+    Fd, Gd = dev(S, F), dev(S, np.zeros_like(F))
+    _lib.check(_lib.lib.sgc_apply_curl(C.c_void_p(Gd.ptr), C.c_void_p(Fd.ptr), 0, S.SGC_C128, 3, int64s(N),
+                                       ints(isfwd), arr, cc, ints(isbloch), scalars2(e), ints([1, 2, 3]), 3,
+                                       ints([1, 2, 3]), 3, ints([1, 2, 3]), scalar2(1.0), stream_handle()))
+    assert_parity(Gd.numpy(), Gref, "sgc_apply_curl one-shot", exact=True)
+    # divergence / gradient / mean one-shots
+    gref = np.zeros(N, dtype=complex, order="F")
+    O.apply_divg(gref, F, "=", isfwd, dlinv, isbloch, e)
+    gd = dev(S, np.zeros(N, dtype=complex))
+    _lib.check(_lib.lib.sgc_apply_divg(C.c_void_p(gd.ptr), C.c_void_p(Fd.ptr), 0, S.SGC_C128, 3, int64s(N),
+                                       ints(isfwd), arr, cc, ints(isbloch), scalars2(e), scalar2(1.0), stream_handle()))
+    assert_parity(gd.numpy(), gref, "sgc_apply_divg one-shot", exact=True)
+    f = rand_field(rng, N, True)
+    Gref = np.zeros_like(F)
+    O.apply_grad(Gref, f, "=", isfwd, dlinv, isbloch, e)
+    _lib.check(_lib.lib.sgc_apply_grad(C.c_void_p(Gd.ptr), C.c_void_p(dev(S, f).ptr), 0, S.SGC_C128, 3, int64s(N),
+                                       ints(isfwd), arr, cc, ints(isbloch), scalars2(e), scalar2(1.0), stream_handle()))
+    assert_parity(Gd.numpy(), Gref, "sgc_apply_grad one-shot", exact=True)
+    Gref = np.zeros_like(F)
+    O.apply_mean(Gref, F, "=", isfwd, None, None, isbloch, e)
+    _lib.check(_lib.lib.sgc_apply_mean(C.c_void_p(Gd.ptr), C.c_void_p(Fd.ptr), 0, S.SGC_C128, 3, int64s(N),
+                                       ints(isfwd), None, None, 0, ints(isbloch), scalars2(e), scalar2(1.0),
+                                       stream_handle()))
+    assert_parity(Gd.numpy(), Gref, "sgc_apply_mean one-shot")
+    fu = np.asfortranarray(F[..., 0])
+    gref = np.zeros(N, dtype=complex, order="F")
+    O.apply_mhat(gref, fu, "=", 2, False, None, None, True, e[1])
+    _lib.check(_lib.lib.sgc_apply_mhat(C.c_void_p(gd.ptr), C.c_void_p(dev(S, fu).ptr), 0, S.SGC_C128, 3, int64s(N),
+                                       2, 0, None, None, 0, 1, scalar2(e[1]), scalar2(1.0), stream_handle()))
+    assert_parity(gd.numpy(), gref, "sgc_apply_mhat one-shot")
+    # host arrays through sgc_op_apply_host (the strict drop-in form for Julia `Array`s)
+    o = S.Operator.curl(S.SGC_C128, N, isfwd, dlinv, isbloch, e)
+    Gh = rand_field(rng, N + (3,), True)
+    Gref = Gh.copy(order="F")
+    O.apply_curl(Gref, F, "+=", isfwd, dlinv, isbloch, e)
+    o.apply_host(Gh, F, "+=")
+    assert_parity(Gh, Gref, "apply_host", exact=True)
+    o.destroy()
+
+
+def test_full_size_properties_256(S):
+    """BASELINE config 2 size (256³, ComplexF64): size-independent properties instead of the
+    oracle — linearity, curl of a constant field vanishes under periodic BCs, div(curl) == 0
+    exactly on a uniform grid (test/divergence.jl:59-74), '+=' twice == '=' with 2α."""
+    import torch
+    N = (256, 256, 256)
+    M = N[0] * N[1] * N[2]
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    F = S.DeviceArray(torch.complex(torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) - 0.5,
+                                    torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) - 0.5), N + (3,))
+    isfwd = [True, True, True]
+    curl = S.Operator.curl(S.SGC_C128, N, isfwd)
+    G = S.DeviceArray.empty(N + (3,))
+    curl.apply(G, F, "=")
+    # constant field → zero curl
+    Cst = S.DeviceArray(torch.full((3 * M,), 0.25 - 0.5j, dtype=torch.complex128, device="cuda"), N + (3,))
+    Gc = S.DeviceArray.empty(N + (3,))
+    curl.apply(Gc, Cst, "=")
+    assert float(Gc.t.abs().max()) == 0.0
+    # div(curl F) == 0 exactly on the uniform periodic grid
+    divg = S.Operator.divg(S.SGC_C128, N, isfwd)
+    d = S.DeviceArray.empty(N)
+    divg.apply(d, G, "=")
+    scale = float(G.t.abs().max())
+    assert float(d.t.abs().max()) <= 16 * np.finfo(float).eps * scale
+    # '+=' accumulates: G2 = 0; G2 += curl F; G2 += curl F  ==  2 * G   (exact: doubling is exact)
+    G2 = S.DeviceArray.zeros(N + (3,))
+    curl.apply(G2, F, "+=")
+    curl.apply(G2, F, "+=")
+    assert torch.equal(G2.t, 2 * G.t)
+    # fused vs unfused sweeps at full size
+    curl.set_tuning(0, 0, 0, 2)
+    G3 = S.DeviceArray.empty(N + (3,))
+    curl.apply(G3, F, "=")
+    assert torch.equal(G3.t, G.t)
