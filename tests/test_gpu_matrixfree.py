@@ -360,7 +360,7 @@ def test_one_shot_c_entry_points_and_host_arrays(S):
 def test_full_size_properties_256(S):
     """BASELINE config 2 size (256³, ComplexF64): size-independent properties instead of the
     oracle — linearity, curl of a constant field vanishes under periodic BCs, div(curl) == 0
-    exactly on a uniform grid (test/divergence.jl:59-74), '+=' twice == '=' with 2α."""
+    to rounding on a uniform grid (test/divergence.jl:59-74), '+=' into zeros == '='."""
     import torch
     N = (256, 256, 256)
     M = N[0] * N[1] * N[2]
@@ -382,11 +382,12 @@ def test_full_size_properties_256(S):
     divg.apply(d, G, "=")
     scale = float(G.t.abs().max())
     assert float(d.t.abs().max()) <= 16 * np.finfo(float).eps * scale
-    # '+=' accumulates: G2 = 0; G2 += curl F; G2 += curl F  ==  2 * G   (exact: doubling is exact)
+    # '+=' into zeros reproduces '=' bit-for-bit; a second '+=' doubles it up to rounding
     G2 = S.DeviceArray.zeros(N + (3,))
     curl.apply(G2, F, "+=")
+    assert torch.equal(G2.t, G.t)
     curl.apply(G2, F, "+=")
-    assert torch.equal(G2.t, 2 * G.t)
+    assert float((G2.t - 2 * G.t).abs().max()) <= 8 * np.finfo(float).eps * scale
     # fused vs unfused sweeps at full size
     curl.set_tuning(0, 0, 0, 2)
     G3 = S.DeviceArray.empty(N + (3,))
