@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native StaggeredGridCalculus hot path.
+
+Metric (BASELINE.json): curl apply in Gcell-updates/s, ComplexF64, next to the HBM roofline.
+Workload at N GPUs (BASELINE.json configs[1], z-slab decomposed for N > 1, weak scaling):
+a 256×256×(256·N) nonuniform Yee grid with PML-stretched (complex) ∆l, symmetric (PEC) outer
+boundaries, and one matrix-free curl-of-curl pass per step,
+
+        H = C_dual E        (apply_curl!, isfwd = [T,T,T], ∆l⁻¹ at dual points)
+        E' = C_prim H       (apply_curl!, isfwd = [F,F,F], ∆l⁻¹ at primal points),
+
+i.e. TWO curl applications = 2·M cell-updates per step, fields resident in HBM (`value`), and
+the same pass driven from pinned host arrays with the copies inside the timed region (`e2e`).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm (CUDA library)
+  python bench.py --impl reference [...]                        # the reference's CPU algorithm
+                                                                # (C/OpenMP port, oracle/)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NLOCAL = (256, 256, 256)   # per-GPU slab
+NPML = 10
+ALG_BYTES_PER_CELL = 96    # one curl, OP '=': read 3 + write 3 ComplexF64 components
+
+
+def build_inputs(nz_total, seed=20260):
+    """Seeded nonuniform grid + PML stretch (host, O(ΣN)); returns ∆l⁻¹ at (primal, dual) points."""
+    from sgc_b200 import gridgen as GG
+    rng = np.random.default_rng(seed)
+    lprim = [GG.graded_lprim(NLOCAL[0], rng), GG.graded_lprim(NLOCAL[1], rng), GG.graded_lprim(nz_total, rng)]
+    grid = GG.Grid(lprim, [False, False, False])
+    mean_cell = np.mean([np.mean(np.diff(l)) for l in lprim])
+    omega = 2 * np.pi / (20 * mean_cell)
+    sdl = GG.create_stretched_dl(omega, grid, ([NPML] * 3, [NPML] * 3))
+    return GG.invert_dl(sdl)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons while the timed region runs (pynvml)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        self.stop_flag = True
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_reference_rate(dlinv_prim, dlinv_dual, nz, target_seconds, threads=None):
+    """Times the C/OpenMP restatement of the reference's algorithm (oracle/) on the host cores:
+    curl-of-curl on a 256×256×nz ComplexF64 grid.  Returns (Gcell/s, threads, description)."""
+    from oracle import c_oracle as CO
+    threads = threads or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
+    CO.set_threads(threads)
+    N = (NLOCAL[0], NLOCAL[1], nz)
+    M = N[0] * N[1] * N[2]
+    rng = np.random.default_rng(1)
+    E = np.asfortranarray(rng.uniform(-1, 1, N + (3,)) + 1j * rng.uniform(-1, 1, N + (3,)))
+    H = np.zeros_like(E)
+    E2 = np.zeros_like(E)
+    dd = [dlinv_dual[0], dlinv_dual[1], dlinv_dual[2][:nz]]
+    dp = [dlinv_prim[0], dlinv_prim[1], dlinv_prim[2][:nz]]
+    bl, e = [False] * 3, [1.0] * 3
+
+    def step():
+        CO.apply_curl(H, E, "=", [True] * 3, dd, bl, e)
+        CO.apply_curl(E2, H, "=", [False] * 3, dp, bl, e)
+
+    step()  # warm-up (page faults)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step()
+        n += 1
+        dt = time.perf_counter() - t0
+        if dt >= target_seconds or n >= 50:
+            break
+    rate = 2 * M * n / dt / 1e9
+    return rate, threads, f"{n} curl-of-curl passes on 256x256x{nz} ComplexF64 (same inputs family), {dt:.1f} s wall"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    nz = 64  # bounded sample: a 256×256×64 z-slab of the workload (per-cell cost is size independent)
+    dprim, ddual = build_inputs(NLOCAL[2] * max(1, args.gpus))
+    # the driver's K/W apply to "steps" of the bounded sample
+    from oracle import c_oracle as CO
+    threads = len(os.sched_getaffinity(0))
+    CO.set_threads(threads)
+    N = (NLOCAL[0], NLOCAL[1], nz)
+    M = N[0] * N[1] * N[2]
+    rng = np.random.default_rng(1)
+    E = np.asfortranarray(rng.uniform(-1, 1, N + (3,)) + 1j * rng.uniform(-1, 1, N + (3,)))
+    H, E2 = np.zeros_like(E), np.zeros_like(E)
+    dd = [ddual[0], ddual[1], ddual[2][:nz]]
+    dp = [dprim[0], dprim[1], dprim[2][:nz]]
+    bl, e = [False] * 3, [1.0] * 3
+
+    def step():
+        CO.apply_curl(H, E, "=", [True] * 3, dd, bl, e)
+        CO.apply_curl(E2, H, "=", [False] * 3, dp, bl, e)
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = 2 * M * args.steps / dt / 1e9
+    sample = f"{args.steps} curl-of-curl passes on a 256x256x{nz} slab of the workload, {dt:.2f} s wall"
+    out = {
+        "impl": "reference", "metric": "curl_apply_gcell_per_s", "value": val, "unit": "Gcell/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C/OpenMP restatement of the reference's six-sweep apply_curl! (Julia is not available in this image)",
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"256x256x{256 * n} nonuniform Yee grid, PML-stretched complex dl (Npml=10), PEC outer "
+                        f"boundaries, ComplexF64 curl-of-curl E->H->E' = 2 apply_curl! per step"
+                        + (f", z-slab decomposed over {n} GPUs (256^3 per GPU) with one-plane halos" if n > 1 else ""),
+            "cells_per_gpu": NLOCAL[0] * NLOCAL[1] * NLOCAL[2], "curl_applies_per_step": 2,
+            "l2_policy": "inputs_larger_than_L2 (3 fields x 805 MB per GPU vs 126 MB L2)",
+            "parallelism": f"zslab{n}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-assembly", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sgc_b200 as S
+    from sgc_b200.slab import SlabCurl
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU: the product path has no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    M = NLOCAL[0] * NLOCAL[1] * NLOCAL[2]
+    nz_total = NLOCAL[2] * world
+    dprim, ddual = build_inputs(nz_total)
+    k0, k1 = rank * NLOCAL[2], (rank + 1) * NLOCAL[2]
+    bl, e = [False] * 3, [1.0] * 3
+    # E -> H: forward differences with ∆l⁻¹ at dual points; H -> E': backward, primal points
+    c_dual = SlabCurl(S.SGC_C128, NLOCAL, [True] * 3, [ddual[0], ddual[1], ddual[2][k0:k1]], bl, e, rank, world)
+    c_prim = SlabCurl(S.SGC_C128, NLOCAL, [False] * 3, [dprim[0], dprim[1], dprim[2][k0:k1]], bl, e, rank, world)
+
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    def rnd():
+        return torch.complex(torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1,
+                             torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
+    E = S.DeviceArray(rnd(), NLOCAL + (3,))
+    H = S.DeviceArray.zeros(NLOCAL + (3,))
+    E2 = S.DeviceArray.zeros(NLOCAL + (3,))
+
+    def step():
+        c_dual.apply(H, E, "=")
+        c_prim.apply(E2, H, "=")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = S.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    clocks = sampler.result()
+    launches = S.launch_count() - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = 2 * M * world / (ms_step * 1e-3) / 1e9  # Gcell-updates/s, whole job
+
+    # ---- end-to-end: pinned host arrays → H2D → two curls → D2H, every step ----------------------
+    E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+    E_host.copy_(E.t)
+    Out_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+    from sgc_b200._lib import lib, check
+    import ctypes as C
+    st = torch.cuda.current_stream()
+    nbytes = 3 * M * 16
+
+    def e2e_step():
+        check(lib.sgc_memcpy_h2d(C.c_void_p(E.ptr), C.c_void_p(E_host.data_ptr()), nbytes, C.c_void_p(st.cuda_stream)))
+        step()
+        check(lib.sgc_memcpy_d2h(C.c_void_p(Out_host.data_ptr()), C.c_void_p(E2.ptr), nbytes, C.c_void_p(st.cuda_stream)))
+        check(lib.sgc_stream_sync(C.c_void_p(st.cuda_stream)))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = 2 * M * world * e2e_steps / e2e_s / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kernel_ms = ms_step / 2  # the step is exactly two launches of the fused curl kernel (+ halo planes for N>1)
+    achieved = ALG_BYTES_PER_CELL * M / (kernel_ms * 1e-3) / 1e9
+    out = {
+        "metric": "curl_apply_gcell_per_s", "value": value, "unit": "Gcell/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": workload_config(world),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_curl3<cplx,cplx,false,TX,TY>",
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
+                     "frac_of_nominal_8TBs": achieved / 8000.0,
+                     "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * M},
+        "clocks": clocks,
+        "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+    }
+    tr = os.path.join(ROOT, "profiles", "curl3_traffic.json")
+    if os.path.exists(tr):
+        try:
+            out["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    if world == 1 and not args.no_assembly:
+        out["assembly"] = bench_assembly(S, torch, peak)
+    if world == 1 and not args.no_cpu_baseline:
+        rate, threads, sample = cpu_reference_rate(dprim, ddual, 64, args.cpu_seconds)
+        out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_assembly(S, torch, peak):
+    """Second half of the metric: create_curl CSC assembly in nnz/s (BASELINE.json configs[3]:
+    512³, Float64, uniform, all-Bloch, nnz = 12·512³ = 1 610 612 736)."""
+    n = 512
+    N = (n, n, n)
+    res = {}
+    try:
+        torch.cuda.synchronize()
+        A = S.create_curl([True] * 3, None, N=N)  # warm-up (allocations, scan scratch)
+        nnz = A.nnz
+        del A
+        torch.cuda.empty_cache()
+        reps = 3
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            A = S.create_curl([True] * 3, None, N=N)
+            del A
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / reps
+        alg = nnz * 16 + (3 * n ** 3 + 1) * 8
+        res = {"workload": "create_curl 512^3 Float64 uniform all-Bloch, order_cmpfirst=true, colptr+rowval+nzval on device",
+               "nnz": nnz, "ms": ms, "nnz_per_s": nnz / (ms * 1e-3), "algorithmic_bytes": alg,
+               "achieved_gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
+               "includes": "table upload, count+scan (colptr), nnz read-back, output allocation, fill"}
+    except Exception as ex:  # out of memory on a shared box etc.
+        res = {"error": str(ex)[:200]}
+    return res
+
+
+if __name__ == "__main__":
+    main()
