@@ -391,4 +391,297 @@ __global__ void __launch_bounds__(TX *TY, (TX * TY <= 256) ? 2 : 1) k_curl3(cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fused full 3-D curl, version 2: z-planes staged through a shared-memory ring by cp.async
+// ---------------------------------------------------------------------------------------------
+// Same mathematics and the same CurlParams as k_curl3.  The difference is how HBM latency is
+// hidden: instead of holding the next plane in registers (which costs occupancy), every z-plane
+// of the CTA's (TX+1)×(TY+1) tile — own cells plus the one-cell x/y halos — is copied
+// global→shared by `cp.async` into a ring of S stages, S−2 planes ahead of the plane being
+// computed.  Bytes in flight are then bounded by shared memory, not by registers.
+//
+//   plane slot j (j = 0..n) holds grid plane  base + j,  base = k0 (forward ∂z) or k0−1 (backward);
+//   output plane k0+t uses  lo = slot t,  hi = slot t+1,  centre = lo (forward) / hi (backward).
+//   Fz and the x/y halos are only needed on centre planes and are only copied for those.
+//
+// One __syncthreads per plane.  x-neighbours still travel by warp shuffle; only the lane at the
+// warp / tile edge reads the halo column from shared memory.
+
+SGC_D void cp_async_elem(cplx *dst_smem, const cplx *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+SGC_D void cp_async_elem(double *dst_smem, const double *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+SGC_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+SGC_D void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// General (boundary-aware) evaluation of one cell of plane k from the staged planes.  This is
+// the code path of k_curl3 with the neighbours coming from shared memory.
+template <typename T, typename C>
+struct CurlCellBC {
+    int xkind, ykind;        // 0 plain, 1 Bloch wrap, 2 symmetric
+    bool x_lo_zero, y_lo_zero;
+};
+
+template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, bool XSHFL>
+__global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__ CurlParams<T, C> p) {
+    static_assert(TX % 32 == 0, "a warp must lie inside one row");
+    static_assert(TX * TY >= 2 * TX + 2 * TY, "not enough threads for the halo copies");
+    static_assert(S >= 3, "need at least 3 stages");
+    constexpr int PITCH = TX + 1;
+    constexpr int COMP = (TY + 1) * PITCH;
+    constexpr int STAGE = 3 * COMP;
+    extern __shared__ __align__(16) unsigned char sgc_smem_raw[];
+    T *const sm = reinterpret_cast<T *>(sgc_smem_raw);
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int lane = tx & 31;
+    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz;
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int i = i0 + tx, j = j0 + ty;
+    const bool valid = (i < Nx) && (j < Ny);
+    const int nvx = min(TX, Nx - i0), nvy = min(TY, Ny - j0);  // valid extent of this tile
+    const int64_t sy = Nx, sz = (int64_t)Nx * Ny;
+    const int64_t ij = (int64_t)j * sy + i;
+    const int fx = p.fwd[0], fy = p.fwd[1], fz = p.fwd[2];
+    // a tile that touches no x/y boundary and is full needs no boundary logic at all
+    const bool tile_plain = (i0 > 0) && (i0 + TX < Nx) && (j0 > 0) && (j0 + TY < Ny);
+
+    // shared-tile coordinates: the halo row/column sits right after the last valid row/column
+    // (forward) or at index 0 (backward)
+    const int self = (ty + (fy ? 0 : 1)) * PITCH + (tx + (fx ? 0 : 1));
+    const int ynb = self + (fy ? PITCH : -PITCH);
+    const int xnb = self + (fx ? 1 : -1);
+
+    // ---- x / y boundary description of this thread (identical to k_curl3) ------------------------
+    int xkind = 0, ykind = 0;  // 0 plain, 1 Bloch wrap, 2 symmetric
+    bool x_lo_zero = false, y_lo_zero = false;
+    if (!tile_plain) {
+        if (fx) { if (i == Nx - 1) xkind = (p.bc_hi[0] == BC_BLOCH) ? 1 : 2; }
+        else    { if (i == 0) xkind = (p.bc_lo[0] == BC_BLOCH) ? 1 : 2; }
+        if (fy) { if (j == Ny - 1) ykind = (p.bc_hi[1] == BC_BLOCH) ? 1 : 2; }
+        else    { if (j == 0) ykind = (p.bc_lo[1] == BC_BLOCH) ? 1 : 2; }
+        x_lo_zero = fx && (i == 0) && (p.bc_lo[0] == BC_SYM);
+        y_lo_zero = fy && (j == 0) && (p.bc_lo[1] == BC_SYM);
+    }
+    // the lane whose x-neighbour is not in its own warp reads it from the shared tile
+    const bool xedge = fx ? (lane == 31 || tx == nvx - 1) : (lane == 0);
+
+    // ---- halo copy duty of this thread (at most one element per plane) ---------------------------
+    const int lin = ty * TX + tx;
+    int hcomp = -1, hdst = 0;
+    int64_t hsrc = 0;
+    if (lin < 2 * TX) {  // y-halo row of Fx (lin < TX) and Fz
+        const int x = (lin < TX) ? lin : lin - TX;
+        if (x < nvx) {
+            int hj = fy ? j0 + nvy : j0 - 1;
+            bool ok = true;
+            if (hj >= Ny) { hj = 0; ok = (p.bc_hi[1] == BC_BLOCH); }
+            if (hj < 0) { hj = Ny - 1; ok = (p.bc_lo[1] == BC_BLOCH); }
+            if (ok) {
+                hcomp = (lin < TX) ? 0 : 2;
+                hdst = (fy ? nvy : 0) * PITCH + (x + (fx ? 0 : 1));
+                hsrc = (int64_t)hj * sy + (i0 + x);
+            }
+        }
+    } else if (lin < 2 * TX + 2 * TY) {  // x-halo column of Fy and Fz
+        const int q = lin - 2 * TX;
+        const int y = (q < TY) ? q : q - TY;
+        if (y < nvy) {
+            int hi = fx ? i0 + nvx : i0 - 1;
+            bool ok = true;
+            if (hi >= Nx) { hi = 0; ok = (p.bc_hi[0] == BC_BLOCH); }
+            if (hi < 0) { hi = Nx - 1; ok = (p.bc_lo[0] == BC_BLOCH); }
+            if (ok) {
+                hcomp = (q < TY) ? 1 : 2;
+                hdst = (y + (fy ? 0 : 1)) * PITCH + (fx ? nvx : 0);
+                hsrc = (int64_t)(j0 + y) * sy + hi;
+            }
+        }
+    }
+    const T *const hbase = (hcomp >= 0) ? p.F[hcomp] + hsrc : nullptr;
+    T *const hsm = sm + (hcomp >= 0 ? hcomp * COMP + hdst : 0);
+
+    const C cxi = valid ? p.c[0][i] : C{};
+    const C cyj = valid ? p.c[1][j] : C{};
+    // backward difference c·(cur − nb) == (−c)·(nb − cur) exactly: fold the direction into the sign
+    const C cxs = fx ? cxi : neg(cxi);
+    const C cys = fy ? cyj : neg(cyj);
+
+    const int k0 = p.k_begin + blockIdx.z * p.march;
+    const int k1 = min(k0 + p.march, p.k_end);
+    if (k0 >= k1) return;
+    const int n = k1 - k0;              // planes to produce
+    const int base = fz ? k0 : k0 - 1;  // grid plane of slot 0
+    const T Z = zero_of(T{});
+
+    // running state of the producer side: slot index, its ring stage, its grid plane offset
+    int jj_issue = 0;
+    int stage_issue = 0;
+    int64_t off_issue = (int64_t)base * sz;  // element offset of the plane of slot jj_issue
+    auto issue = [&]() {
+        if (jj_issue <= n) {
+            T *st = sm + stage_issue * STAGE;
+            const int kp = base + jj_issue;
+            const bool centre = fz ? (jj_issue < n) : (jj_issue >= 1);
+            if (kp >= 0 && kp < Nz) {
+                if (valid) {
+                    cp_async_elem(st + self, p.F[0] + off_issue + ij);
+                    cp_async_elem(st + COMP + self, p.F[1] + off_issue + ij);
+                    if (centre) cp_async_elem(st + 2 * COMP + self, p.F[2] + off_issue + ij);
+                }
+                if (centre && hcomp >= 0) cp_async_elem(hsm + stage_issue * STAGE, hbase + off_issue);
+            } else if (valid) {  // plane outside the slab: wrap-around plane or the neighbour rank's plane
+                cp_async_elem(st + self, p.ghost[0] + ij);
+                cp_async_elem(st + COMP + self, p.ghost[1] + ij);
+            }
+        }
+        cp_async_commit();
+        ++jj_issue;
+        off_issue += sz;
+        stage_issue = (stage_issue + 1 == S) ? 0 : stage_issue + 1;
+    };
+
+#pragma unroll
+    for (int q = 0; q < S - 1; ++q) issue();
+
+    T xlo = Z, ylo = Z;
+    int stage_lo = 0;
+    int64_t off_out = (int64_t)k0 * sz + ij;
+    for (int t = 0; t < n; ++t, off_out += sz) {
+        const int k = k0 + t;
+        T g0 = Z, g1 = Z, g2 = Z;
+        if (ADD && valid) {  // issue the read-modify-write loads early
+            g0 = ldg_plain(p.G[0] + off_out); g1 = ldg_plain(p.G[1] + off_out); g2 = ldg_plain(p.G[2] + off_out);
+        }
+        cp_async_wait<S - 3>();  // slots ≤ t+1 have landed (for this thread) ...
+        __syncthreads();         // ... and for everybody; everybody has also finished plane t−1
+        issue();                 // refill the stage that plane t−1 used
+
+        const int stage_hi = (stage_lo + 1 == S) ? 0 : stage_lo + 1;
+        const T *slo = sm + stage_lo * STAGE;
+        const T *shi = sm + stage_hi * STAGE;
+        const T *sc = fz ? slo : shi;
+        stage_lo = stage_hi;
+        if (t == 0) { xlo = slo[self]; ylo = slo[COMP + self]; }
+        const T xhi = shi[self], yhi = shi[COMP + self];
+        const T xc = fz ? xlo : xhi;
+        const T yc = fz ? ylo : yhi;
+        const T zc = sc[2 * COMP + self];
+        const C czk = p.c[2][k];
+        T gx, gy, gz;
+
+        if (tile_plain && k > 0 && k < Nz - 1) {
+            // ---- fast path: no boundary in reach; every term is c·(nb − cur) ------------------------
+            const T xn = sc[ynb], zn = sc[2 * COMP + ynb];
+            T yn, zx;
+            if (XSHFL) {
+                yn = fx ? shfl_down1(yc) : shfl_up1(yc);
+                zx = fx ? shfl_down1(zc) : shfl_up1(zc);
+                if (xedge) { yn = sc[COMP + xnb]; zx = sc[2 * COMP + xnb]; }
+            } else {
+                yn = sc[COMP + xnb];
+                zx = sc[2 * COMP + xnb];
+            }
+            const T dzx = mul(czk, sub(xhi, xlo));
+            const T dzy = mul(czk, sub(yhi, ylo));
+            const T dyx = mul(cys, sub(xn, xc));
+            const T dyz = mul(cys, sub(zn, zc));
+            const T dxy = mul(cxs, sub(yn, yc));
+            const T dxz = mul(cxs, sub(zx, zc));
+            if (ADD) {
+                gx = add(add(g0, neg(dzy)), dyz);
+                gy = add(add(g1, dzx), neg(dxz));
+                gz = add(add(g2, neg(dyx)), dxy);
+            } else {
+                gx = add(add(Z, neg(dzy)), dyz);
+                gy = add(dzx, neg(dxz));
+                gz = add(neg(dyx), dxy);
+            }
+        } else {
+            // ---- general path: boundary rules folded in (same code as k_curl3) -----------------------
+            T dzx, dzy;
+            {
+                T xh = xhi, yh = yhi, xl = xlo, yl = ylo;
+                bool zero_term = false;
+                if (fz) {
+                    if (k == Nz - 1) {
+                        if (p.bc_hi[2] == BC_BLOCH) { xh = mul_e(p.e[2], xh, p.e_real[2]); yh = mul_e(p.e[2], yh, p.e_real[2]); }
+                        else if (p.bc_hi[2] == BC_SYM) { xh = Z; yh = Z; }
+                    }
+                    if (k == 0 && p.bc_lo[2] == BC_SYM) { xl = Z; yl = Z; }
+                } else if (k == 0) {
+                    if (p.bc_lo[2] == BC_BLOCH) { xl = div_e(xl, p.e[2], p.e_real[2]); yl = div_e(yl, p.e[2], p.e_real[2]); }
+                    else if (p.bc_lo[2] == BC_SYM) zero_term = true;
+                }
+                dzx = zero_term ? Z : mul(czk, sub(xh, xl));
+                dzy = zero_term ? Z : mul(czk, sub(yh, yl));
+            }
+            T dyx, dyz;
+            {
+                const T xn = sc[ynb], zn = sc[2 * COMP + ynb];
+                T xh, xl, zh, zl;
+                bool zero_term = false;
+                if (fy) {
+                    xh = xn; zh = zn; xl = xc; zl = zc;
+                    if (ykind == 1) { xh = mul_e(p.e[1], xh, p.e_real[1]); zh = mul_e(p.e[1], zh, p.e_real[1]); }
+                    else if (ykind == 2) { xh = Z; zh = Z; }
+                    if (y_lo_zero) { xl = Z; zl = Z; }
+                } else {
+                    xh = xc; zh = zc; xl = xn; zl = zn;
+                    if (ykind == 1) { xl = div_e(xl, p.e[1], p.e_real[1]); zl = div_e(zl, p.e[1], p.e_real[1]); }
+                    else if (ykind == 2) zero_term = true;
+                }
+                dyx = zero_term ? Z : mul(cyj, sub(xh, xl));
+                dyz = zero_term ? Z : mul(cyj, sub(zh, zl));
+            }
+            T dxy, dxz;
+            {
+                T yn = sc[COMP + xnb], zn = sc[2 * COMP + xnb];
+                if (XSHFL) {
+                    const T ys = fx ? shfl_down1(yc) : shfl_up1(yc);
+                    const T zs = fx ? shfl_down1(zc) : shfl_up1(zc);
+                    if (!xedge) { yn = ys; zn = zs; }
+                }
+                T yh, yl, zh, zl;
+                bool zero_term = false;
+                if (fx) {
+                    yh = yn; zh = zn; yl = yc; zl = zc;
+                    if (xkind == 1) { yh = mul_e(p.e[0], yh, p.e_real[0]); zh = mul_e(p.e[0], zh, p.e_real[0]); }
+                    else if (xkind == 2) { yh = Z; zh = Z; }
+                    if (x_lo_zero) { yl = Z; zl = Z; }
+                } else {
+                    yh = yc; zh = zc; yl = yn; zl = zn;
+                    if (xkind == 1) { yl = div_e(yl, p.e[0], p.e_real[0]); zl = div_e(zl, p.e[0], p.e_real[0]); }
+                    else if (xkind == 2) zero_term = true;
+                }
+                dxy = zero_term ? Z : mul(cxi, sub(yh, yl));
+                dxz = zero_term ? Z : mul(cxi, sub(zh, zl));
+            }
+            if (ADD) {
+                gx = add(add(g0, neg(dzy)), dyz);
+                gy = add(add(g1, dzx), neg(dxz));
+                gz = add(add(g2, neg(dyx)), dxy);
+            } else {
+                gx = add(add(Z, neg(dzy)), dyz);
+                gy = add(dzx, neg(dxz));
+                gz = add(neg(dyx), dxy);
+            }
+        }
+        if (valid) {
+            stg_stream(p.G[0] + off_out, gx);
+            stg_stream(p.G[1] + off_out, gy);
+            stg_stream(p.G[2] + off_out, gz);
+        }
+        xlo = xhi;
+        ylo = yhi;
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace sgc

@@ -461,6 +461,8 @@ static int launch_zero(const sgc_op *op, T *G, int64_t k_begin, int64_t k_end, c
 
 template <typename T, typename C, bool ADD>
 static void launch_curl3_tiles(const CurlParams<T, C> &p, int tx, int ty, dim3 grid_xy_z, cudaStream_t st);
+template <typename T, typename C, bool ADD>
+static int launch_curl3p_tiles(const CurlParams<T, C> &p, int tx, int ty, int stages, int minb, bool xshfl, dim3 grid, cudaStream_t st);
 
 template <typename T, typename C>
 static int launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghost, bool add_mode,
@@ -490,22 +492,73 @@ static int launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *g
     p.Nx = (int)op->N[0]; p.Ny = (int)op->N[1]; p.Nz = (int)op->N[2];
     p.k_begin = (int)k_begin; p.k_end = (int)k_end;
 
+    const int kernel_variant = op->variant & 0xF;
+    // defaults from the 256^3 sweep on B200 (profiles/r1_sweep_curl.md): 32x4 tiles, 4-stage ring,
+    // 4 CTAs/SM (128 registers, no spills), 16-plane z-march
     int tx = op->tile_x ? op->tile_x : 32;
-    int ty = op->tile_y ? op->tile_y : 8;
+    int ty = op->tile_y ? op->tile_y : (kernel_variant == 1 ? 8 : 4);
     const int64_t gx = (p.Nx + tx - 1) / tx, gy = (p.Ny + ty - 1) / ty;
     const int64_t nk = k_end - k_begin;
     int march = op->march;
     if (march <= 0) {
-        const int64_t want = 148 * 12;  // ≥ ~4 waves of 3 CTAs/SM
-        const int64_t zch = std::max<int64_t>(1, (want + gx * gy - 1) / (gx * gy));
-        march = (int)std::max<int64_t>(8, std::min<int64_t>(64, nk / zch));
+        if (kernel_variant == 1) {
+            const int64_t want = 148 * 12;  // ≥ ~4 waves of 3 CTAs/SM
+            const int64_t zch = std::max<int64_t>(1, (want + gx * gy - 1) / (gx * gy));
+            march = (int)std::max<int64_t>(8, std::min<int64_t>(64, nk / zch));
+        } else {
+            march = 16;
+        }
     }
     p.march = march;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((nk + march - 1) / march));
     if (grid.y > 65535 || grid.z > 65535) return fail(SGC_ERR_INVALID, "grid too large for the fused curl tiling");
-    if (add_mode) launch_curl3_tiles<T, C, true>(p, tx, ty, grid, st);
-    else launch_curl3_tiles<T, C, false>(p, tx, ty, grid, st);
-    return check_launch("k_curl3");
+    if (kernel_variant == 1) {  // v1: register-prefetch z-march
+        if (add_mode) launch_curl3_tiles<T, C, true>(p, tx, ty, grid, st);
+        else launch_curl3_tiles<T, C, false>(p, tx, ty, grid, st);
+        return check_launch("k_curl3");
+    }
+    const int stages = ((op->variant >> 4) & 0xF) ? ((op->variant >> 4) & 0xF) : 4;
+    int minb = (op->variant >> 8) & 0xF;
+    if (!minb) minb = (tx * ty <= 128) ? 4 : ((tx * ty <= 256) ? 3 : 2);
+    const bool xshfl = ((op->variant >> 12) & 1) == 0;  // bit 12: read x-neighbours from the shared tile instead
+    int s = add_mode ? launch_curl3p_tiles<T, C, true>(p, tx, ty, stages, minb, xshfl, grid, st)
+                     : launch_curl3p_tiles<T, C, false>(p, tx, ty, stages, minb, xshfl, grid, st);
+    if (s) return s;
+    return check_launch("k_curl3p");
+}
+
+// v2: cp.async shared-memory ring.
+template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, bool XSHFL>
+static int launch_curl3p_one(const CurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = (size_t)S * 3 * (TY + 1) * (TX + 1) * sizeof(T);
+    auto kern = k_curl3p<T, C, ADD, TX, TY, S, MINB, XSHFL>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
+    return SGC_OK;
+}
+
+template <typename T, typename C, bool ADD>
+static int launch_curl3p_tiles(const CurlParams<T, C> &p, int tx, int ty, int stages, int minb, bool xshfl, dim3 grid, cudaStream_t st) {
+#define CURLP_CASE(TX, TY, S, MINB) \
+    if (tx == TX && ty == TY && stages == S && minb == MINB)                                                   \
+        return xshfl ? launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, true>(p, grid, st)                        \
+                     : launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, false>(p, grid, st);
+    CURLP_CASE(32, 4, 4, 4)
+    CURLP_CASE(32, 8, 3, 3)
+    CURLP_CASE(32, 8, 4, 3)
+    CURLP_CASE(32, 8, 4, 2)
+    CURLP_CASE(32, 8, 6, 2)
+    CURLP_CASE(32, 16, 3, 2)
+    CURLP_CASE(32, 16, 4, 1)
+    CURLP_CASE(64, 4, 4, 3)
+    CURLP_CASE(64, 4, 4, 2)
+    CURLP_CASE(64, 8, 3, 2)
+#undef CURLP_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl: tile %dx%d, %d stages, %d CTAs/SM is not built", tx, ty, stages, minb);
 }
 
 template <typename T, typename C, bool ADD>
@@ -525,7 +578,7 @@ template <typename T>
 static int apply_typed(const sgc_op *op, T *G, const T *F, int opmode, const void *const *ghost,
                        int64_t k_begin, int64_t k_end, cudaStream_t st) {
     const bool user_add = (opmode == SGC_OP_ADD);
-    if (op->fused_curl && op->variant != 2) {
+    if (op->fused_curl && (op->variant & 0xF) != 2) {
         if constexpr (std::is_same<T, double>::value) {
             return launch_curl3<double, double>(op, G, F, ghost, user_add, k_begin, k_end, st);
         } else {
@@ -583,7 +636,7 @@ extern "C" int sgc_op_apply(const sgc_op *op, void *G, const void *F, int opmode
 
 extern "C" int sgc_op_launches(const sgc_op *op, int opmode) {
     if (!op) return 0;
-    if (op->fused_curl && op->variant != 2) return 1;
+    if (op->fused_curl && (op->variant & 0xF) != 2) return 1;
     int n = 0, cur_out = -1;
     bool add_mode = opmode == SGC_OP_ADD;
     for (const Term &t : op->terms) {

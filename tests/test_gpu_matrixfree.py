@@ -172,11 +172,20 @@ def test_apply_curl_dtypes_and_alpha(S, cplx_field, cplx_coef, alpha):
                 assert_parity(Gd.numpy(), Gref, f"curl dtypes fwd={isfwd} bloch={isbloch} {op}")
 
 
-@pytest.mark.parametrize("tile", [(32, 4), (32, 8), (32, 16), (64, 4), (64, 8)])
+# every instantiated configuration of the fused kernels: (tile_x, tile_y, stages, CTAs/SM) of the
+# cp.async ring kernel (variant 0) with shuffle / shared-memory x-neighbours, and the
+# register-prefetch kernel (variant 1)
+RING_CONFIGS = [(32, 4, 4, 4), (32, 8, 3, 3), (32, 8, 4, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2), (32, 16, 4, 1),
+                (64, 4, 4, 3), (64, 4, 4, 2), (64, 8, 3, 2)]
+FUSED_VARIANTS = [(tx, ty, 0 | (st << 4) | (mb << 8) | (xs << 12)) for (tx, ty, st, mb) in RING_CONFIGS for xs in (0, 1)]
+FUSED_VARIANTS += [(tx, ty, 1) for (tx, ty) in [(32, 4), (32, 8), (32, 16), (64, 4), (64, 8)]]
+
+
+@pytest.mark.parametrize("cfg", FUSED_VARIANTS)
 @pytest.mark.parametrize("march", [1, 3, 64])
-def test_fused_curl_tilings_agree_with_unfused_sweeps(S, tile, march):
-    """Every tiling / z-march length of the fused kernel gives the bits of the per-block sweeps
-    (variant 2 = the reference's own six-sweep structure on the GPU)."""
+def test_fused_curl_tilings_agree_with_unfused_sweeps(S, cfg, march):
+    """Every kernel variant / tiling / ring depth / z-march length of the fused curl gives the
+    bits of the per-block sweeps (variant 2 = the reference's own six-sweep structure on the GPU)."""
     rng = np.random.default_rng(600)
     N = (70, 21, 13)
     F = dev(S, rand_field(rng, N + (3,), True))
@@ -188,13 +197,37 @@ def test_fused_curl_tilings_agree_with_unfused_sweeps(S, tile, march):
         for op in ("=", "+="):
             o = S.Operator.curl(S.SGC_C128, N, isfwd, dlinv, isbloch, e, alpha=0.75)
             Ga, Gb = dev(S, G0), dev(S, G0)
-            o.set_tuning(tile[0], tile[1], march, 0)
+            o.set_tuning(cfg[0], cfg[1], march, cfg[2])
             o.apply(Ga, F, op)
             o.set_tuning(0, 0, 0, 2)
             o.apply(Gb, F, op)
             assert o.launches(op) == (7 if op == "=" else 6)
-            assert_parity(Ga.numpy(), Gb.numpy(), f"fused {tile} march={march} fwd={isfwd} {op}", exact=True)
+            assert_parity(Ga.numpy(), Gb.numpy(), f"fused {cfg} march={march} fwd={isfwd} {op}", exact=True)
             o.destroy()
+
+
+@pytest.mark.parametrize("N", [(200, 150, 40), (97, 130, 33)])
+def test_fused_curl_interior_fast_path_on_larger_grids(S, N):
+    """Grids with many interior tiles (the boundary-free fast path) next to boundary tiles, all
+    BC kinds, Float64 and ComplexF64, against the per-block sweeps bit-for-bit."""
+    rng = np.random.default_rng(601)
+    for cplx in (True, False):
+        F = dev(S, rand_field(rng, N + (3,), cplx))
+        G0 = rand_field(rng, N + (3,), cplx)
+        dlinv = [rand_coef(rng, n, cplx) for n in N]
+        e = [np.exp(-0.5j), np.exp(0.25j), np.exp(-1.0j)] if cplx else [1.0, -1.0, 1.0]
+        for isfwd in itertools.product((False, True), repeat=3):
+            for isbloch in ([True, True, True], [False, False, False]):
+                o = S.Operator.curl(S.SGC_C128 if cplx else S.SGC_F64, N, isfwd, dlinv, isbloch, e)
+                for op in ("=", "+="):
+                    Ga, Gb = dev(S, G0), dev(S, G0)
+                    o.set_tuning(0, 0, 0, 0)
+                    o.apply(Ga, F, op)
+                    o.set_tuning(0, 0, 0, 2)
+                    o.apply(Gb, F, op)
+                    assert_parity(Ga.numpy(), Gb.numpy(), f"fast path N={N} cplx={cplx} fwd={isfwd} bloch={isbloch} {op}",
+                                  exact=True)
+                o.destroy()
 
 
 def test_apply_subcurls_match_oracle(S):
