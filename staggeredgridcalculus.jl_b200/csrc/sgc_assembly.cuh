@@ -47,83 +47,123 @@ struct AsmParams {
 SGC_D bool is_zero(double v) { return v == 0.0; }
 SGC_D bool is_zero(cplx v) { return v.re == 0.0 && v.im == 0.0; }
 
-// The candidate entries of one column, sorted by row.  Returns the count.
+// Subscripts of grid cell c and the block column of matrix column `col`.
 template <typename T, typename IDX>
-SGC_D int column_entries(const AsmParams<T> &p, int64_t col, int64_t *rows, T *vals) {
-    // column → (block column nu, grid cell c)
-    int nu;
-    IDX c;
+SGC_D void column_decode(const AsmParams<T> &p, int64_t col, int &nu, IDX &c, IDX sub[3]) {
     if (p.cmpfirst) {
-        c = (IDX)col / (IDX)p.Kin;
-        nu = (int)((IDX)col - c * (IDX)p.Kin);
+        const IDX kin = (IDX)p.Kin;
+        c = kin == 3 ? (IDX)col / 3 : (kin == 2 ? (IDX)col / 2 : (IDX)col);
+        nu = (int)((IDX)col - c * kin);
     } else {
         nu = (int)((IDX)col / (IDX)p.M);
         c = (IDX)col - (IDX)nu * (IDX)p.M;
     }
-    // grid cell → subscripts
-    IDX sub[3];
     const IDX n0 = (IDX)p.N[0], n1 = (IDX)p.N[1];
-    IDX t = c / n0;
+    const IDX t = c / n0;
     sub[0] = c - t * n0;
     sub[2] = t / n1;
     sub[1] = t - sub[2] * n1;
-    const int64_t stride[3] = {1, p.N[0], p.N[0] * p.N[1]};
+}
 
+// The (≤ 2) triplets block B contributes to the column of grid cell c: value, LOCAL row of the
+// (block of the) matrix, and validity (nonzero value, row inside the partition).
+template <typename T, typename IDX>
+SGC_D void block_entries(const AsmParams<T> &p, const AsmBlock<T> &B, IDX c, const IDX sub[3], T v[2], int64_t r[2],
+                         bool ok[2]) {
+    const int a = B.axis;
+    const int64_t Nw = p.N[a];
+    const int64_t cw = (int64_t)sub[a];
+    const int64_t stride = a == 0 ? 1 : (a == 1 ? p.N[0] : p.N[0] * p.N[1]);
+    ok[0] = true;
+    ok[1] = false;
+    r[0] = (int64_t)c;
+    r[1] = (int64_t)c;
+    v[1] = zero_of(T{});
+    if (B.ns == 0) {  // diagonal-only (create_πcmp)
+        v[0] = B.V0[0];
+    } else if (Nw == 1) {
+        // diagonal and off-diagonal triplets coincide; `sparse` sums them in input order
+        v[0] = add(B.V0[0], B.Vs[0]);
+    } else {
+        // off-diagonal triplet of row r lands in column r shifted by +ns  ⇒  r = c − ns
+        int64_t rw = cw - B.ns;
+        if (rw < 0) rw += Nw;
+        if (rw >= Nw) rw -= Nw;
+        v[0] = B.V0[cw];
+        v[1] = B.Vs[rw];
+        r[1] = (int64_t)c + (rw - cw) * stride;
+        ok[1] = true;
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int64_t grow = p.cmpfirst ? (int64_t)p.Kout * r[q] + B.nv : r[q] + p.M * B.nv;
+        ok[q] = ok[q] && !is_zero(v[q]) && grow >= p.row_begin && grow < p.row_end;  // dropzeros!, partition
+        r[q] = grow - p.row_begin;
+    }
+}
+
+// Number of stored entries of one column.
+template <typename T, typename IDX>
+SGC_D int column_count(const AsmParams<T> &p, int64_t col) {
+    int nu;
+    IDX c, sub[3];
+    column_decode<T, IDX>(p, col, nu, c, sub);
     int cnt = 0;
     for (int b = 0; b < p.nblk; ++b) {
         const AsmBlock<T> &B = p.blk[b];
         if (B.nu != nu) continue;
-        const int a = B.axis;
-        const int64_t Nw = p.N[a];
-        const int64_t cw = (int64_t)sub[a];
         T v[2];
         int64_t r[2];
-        int ne = 0;
-        if (B.ns == 0) {  // diagonal-only (create_πcmp)
-            v[0] = B.V0[0];
-            r[0] = (int64_t)c;
-            ne = 1;
-        } else if (Nw == 1) {
-            // diagonal and off-diagonal triplets coincide; `sparse` sums them in input order
-            v[0] = add(B.V0[0], B.Vs[0]);
-            r[0] = (int64_t)c;
-            ne = 1;
-        } else {
-            // off-diagonal triplet of row r lands in column r shifted by +ns  ⇒  r = c − ns
-            int64_t rw = cw - B.ns;
-            if (rw < 0) rw += Nw;
-            if (rw >= Nw) rw -= Nw;
-            v[0] = B.V0[cw];
-            r[0] = (int64_t)c;
-            v[1] = B.Vs[rw];
-            r[1] = (int64_t)c + (rw - cw) * stride[a];
-            ne = 2;
-        }
-        for (int q = 0; q < ne; ++q) {
-            if (is_zero(v[q])) continue;  // dropzeros!
-            const int64_t grow = p.cmpfirst ? (int64_t)p.Kout * r[q] + B.nv : r[q] + p.M * B.nv;
-            if (grow < p.row_begin || grow >= p.row_end) continue;
-            rows[cnt] = grow - p.row_begin;
-            vals[cnt] = v[q];
-            ++cnt;
-        }
+        bool ok[2];
+        block_entries<T, IDX>(p, B, c, sub, v, r, ok);
+        cnt += (int)ok[0] + (int)ok[1];
     }
-    // sort by row (insertion sort on ≤ 6 register-resident entries)
+    return cnt;
+}
+
+template <typename T>
+SGC_D void cmpswap(int64_t &ra, T &va, int64_t &rb, T &vb) {
+    if (rb < ra) {
+        const int64_t tr = ra; ra = rb; rb = tr;
+        const T tv = va; va = vb; vb = tv;
+    }
+}
+
+// The entries of one column sorted by row, in registers: invalid slots carry row = INT64_MAX and
+// sink to the end of a fixed 6-input sorting network (the "segmented sort" of a ≤ 6-entry
+// column segment).  Returns the count.
+template <typename T, typename IDX>
+SGC_D int column_entries(const AsmParams<T> &p, int64_t col, int64_t (&rows)[ASM_MAX_ENTRIES], T (&vals)[ASM_MAX_ENTRIES]) {
+    int nu;
+    IDX c, sub[3];
+    column_decode<T, IDX>(p, col, nu, c, sub);
+    constexpr int64_t INVALID = 0x7fffffffffffffffLL;
 #pragma unroll
-    for (int a = 1; a < ASM_MAX_ENTRIES; ++a) {
-        if (a < cnt) {
-            int64_t rk = rows[a];
-            T vk = vals[a];
-            int b = a - 1;
-            while (b >= 0 && rows[b] > rk) {
-                rows[b + 1] = rows[b];
-                vals[b + 1] = vals[b];
-                --b;
+    for (int q = 0; q < ASM_MAX_ENTRIES; ++q) { rows[q] = INVALID; vals[q] = zero_of(T{}); }
+    int cnt = 0, slot = 0;  // slot: which pair of the register array the next matching block fills
+    for (int b = 0; b < p.nblk; ++b) {
+        const AsmBlock<T> &B = p.blk[b];
+        if (B.nu != nu) continue;
+        T v[2];
+        int64_t r[2];
+        bool ok[2];
+        block_entries<T, IDX>(p, B, c, sub, v, r, ok);
+        cnt += (int)ok[0] + (int)ok[1];
+        // static register indexing: the block-column has at most 3 blocks
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3)
+            if (slot == s3) {
+                if (ok[0]) { rows[2 * s3] = r[0]; vals[2 * s3] = v[0]; }
+                if (ok[1]) { rows[2 * s3 + 1] = r[1]; vals[2 * s3 + 1] = v[1]; }
             }
-            rows[b + 1] = rk;
-            vals[b + 1] = vk;
-        }
+        ++slot;
     }
+    // 6-input sorting network (12 compare-exchanges)
+    cmpswap(rows[0], vals[0], rows[5], vals[5]); cmpswap(rows[1], vals[1], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[4], vals[4]);
+    cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
+    cmpswap(rows[0], vals[0], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[5], vals[5]);
+    cmpswap(rows[0], vals[0], rows[1], vals[1]); cmpswap(rows[2], vals[2], rows[3], vals[3]); cmpswap(rows[4], vals[4], rows[5], vals[5]);
+    cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
     return cnt;
 }
 
@@ -134,9 +174,7 @@ struct ColumnCount {
     AsmParams<T> p;
     __device__ int64_t operator()(int64_t col) const {
         if (col >= p.ncol) return 0;
-        int64_t rows[ASM_MAX_ENTRIES];
-        T vals[ASM_MAX_ENTRIES];
-        return (int64_t)column_entries<T, IDX>(p, col, rows, vals);
+        return (int64_t)column_count<T, IDX>(p, col);
     }
 };
 
@@ -162,10 +200,12 @@ __global__ void __launch_bounds__(BLOCK) k_asm_fill(const __grid_constant__ AsmP
         T vals[ASM_MAX_ENTRIES];
         const int cnt = column_entries<T, IDX>(p, col, rows, vals);
         const int64_t off = colptr[col] - p.index_base - base;
-        for (int q = 0; q < cnt; ++q) {
-            s_rows[off + q] = rows[q] + p.index_base;
-            s_vals[off + q] = vals[q];
-        }
+#pragma unroll
+        for (int q = 0; q < ASM_MAX_ENTRIES; ++q)
+            if (q < cnt) {
+                s_rows[off + q] = rows[q] + p.index_base;
+                s_vals[off + q] = vals[q];
+            }
     }
     __syncthreads();
     for (int64_t q = threadIdx.x; q < total; q += BLOCK) {

@@ -1,0 +1,290 @@
+# SGCB200.jl — Julia shim: StaggeredGridCalculus.jl's hot-path methods on device arrays,
+# forwarded to libsgc_b200.so through `ccall`.
+#
+# How it plugs in (see INTEGRATION.md): `include` this file at the end of
+# src/StaggeredGridCalculus.jl (after line 17).  It adds METHODS to the reference's own
+# generic functions — same names, same positional/keyword arguments — that are more specific
+# than the reference's `AbsArrNumber` methods because the field arguments are `DeviceArray`s.
+# The reference's wrappers (scalar-∆ `fill.`, `SVec` conversion; e.g.
+# src/matrixfree/differential/curl.jl:12-49) keep working unchanged and dispatch lands here.
+# `create_*` are reached through `create_*(Val(:b200), args...; kwargs...)` or by setting
+# `SGCB200.ASSEMBLE_ON_DEVICE[] = true`, which reroutes the concrete methods.
+#
+# NOTE: there is no Julia runtime in the build image, so this file has never been executed; it
+# is kept deliberately thin — every decision (validation, promotion, kernel choice) lives in the
+# C library, which is exercised through the identical `ctypes` binding by the test-suite.
+#
+# There is no CPU fallback: if the library or a GPU is missing every call throws.
+
+module SGCB200
+
+using SparseArrays
+import ..StaggeredGridCalculus: apply_∂!, apply_m̂!, apply_curl!, apply_divg!, apply_grad!, apply_mean!,
+                                create_∂, create_m̂, create_mean, create_curl, create_divg, create_grad, create_πcmp
+
+const LIB = get(ENV, "SGC_B200_LIB", joinpath(@__DIR__, "..", "csrc", "libsgc_b200.so"))
+const ASSEMBLE_ON_DEVICE = Ref(false)
+
+const SGC_F64, SGC_C128 = Cint(0), Cint(1)
+const SGC_OP_SET, SGC_OP_ADD = Cint(0), Cint(1)
+
+struct SGCError <: Exception
+    code::Cint
+    msg::String
+end
+
+function check(status::Cint)
+    status == 0 && return nothing
+    msg = unsafe_string(ccall((:sgc_last_error, LIB), Cstring, ()))
+    status == 3 && throw(InexactError(:apply, Float64, msg))  # complex α/e/∆ with a Float64 field
+    status == 1 && throw(ArgumentError(msg))                   # the reference's @assert / @error
+    throw(SGCError(status, msg))
+end
+
+dtype_code(::Type{Float64}) = SGC_F64
+dtype_code(::Type{ComplexF64}) = SGC_C128
+opcode(::Val{:(=)}) = SGC_OP_SET
+opcode(::Val{:(+=)}) = SGC_OP_ADD
+
+# ---------------------------------------------------------------------------------------------
+# DeviceArray: a column-major Julia array living in HBM
+# ---------------------------------------------------------------------------------------------
+mutable struct DeviceArray{T<:Union{Float64,ComplexF64},N} <: AbstractArray{T,N}
+    ptr::Ptr{Cvoid}
+    dims::NTuple{N,Int}
+    owner::Any   # parent DeviceArray for views (keeps the allocation alive), `nothing` for owners
+end
+
+function DeviceArray{T}(::UndefInitializer, dims::Vararg{Int,N}) where {T,N}
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:sgc_malloc, LIB), Cint, (Ptr{Ptr{Cvoid}}, Csize_t), p, sizeof(T) * prod(dims)))
+    a = DeviceArray{T,N}(p[], dims, nothing)
+    finalizer(x -> ccall((:sgc_free, LIB), Cint, (Ptr{Cvoid},), x.ptr), a)
+    return a
+end
+
+function DeviceArray(h::Array{T,N}) where {T,N}
+    d = DeviceArray{T}(undef, size(h)...)
+    copyto!(d, h)
+    return d
+end
+
+Base.size(a::DeviceArray) = a.dims
+Base.similar(a::DeviceArray{T}, dims::Dims) where {T} = DeviceArray{T}(undef, dims...)
+Base.getindex(::DeviceArray, I...) = error("scalar indexing of a DeviceArray is not supported; copy to the host with Array(a)")
+
+function Base.copyto!(d::DeviceArray{T}, h::Array{T}) where {T}
+    @assert length(d) == length(h)
+    check(ccall((:sgc_memcpy_h2d, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), d.ptr, h, sizeof(h), C_NULL))
+    check(ccall((:sgc_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    return d
+end
+
+function Base.Array(d::DeviceArray{T,N}) where {T,N}
+    h = Array{T,N}(undef, d.dims)
+    check(ccall((:sgc_memcpy_d2h, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}), h, d.ptr, sizeof(h), C_NULL))
+    check(ccall((:sgc_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    return h
+end
+
+# `selectdim(F, K+1, w)` — the component slices the reference takes (curl.jl:68, :88) are
+# contiguous because the component index is the last (slowest) dimension.
+function Base.selectdim(a::DeviceArray{T,N}, d::Integer, w::Integer) where {T,N}
+    d == N || error("only slices of the last dimension are contiguous")
+    m = prod(a.dims[1:N-1])
+    return DeviceArray{T,N-1}(a.ptr + sizeof(T) * m * (w - 1), a.dims[1:N-1], a)
+end
+
+# ---------------------------------------------------------------------------------------------
+# argument marshalling
+# ---------------------------------------------------------------------------------------------
+pair(x::Number) = (z = ComplexF64(x); Cdouble[real(z), imag(z)])
+pairs(xs) = (v = Cdouble[]; for x in xs; z = ComplexF64(x); push!(v, real(z), imag(z)); end; v)
+cints(xs) = Cint[Cint(x) for x in xs]
+
+# promote a tuple of per-axis vectors to one element type, as the concrete methods'
+# promote_type does (matrix/differential/curl.jl:59)
+function coefs(vs)
+    T = any(v -> eltype(v) <: Complex, vs) ? ComplexF64 : Float64
+    keep = [Vector{T}(v) for v in vs]
+    return keep, Ptr{Cvoid}[pointer(k) for k in keep], Cint(T == ComplexF64)
+end
+
+# ---------------------------------------------------------------------------------------------
+# matrix-free operators
+# ---------------------------------------------------------------------------------------------
+# apply_∂!  — src/matrixfree/differential/partial.jl:33 (3-D), :241 (2-D), :388 (1-D)
+function apply_∂!(Gv::DeviceArray{T,K}, Fu::DeviceArray{T,K}, ::Val{OP}, nw::Integer, isfwd::Bool,
+                  ∆w⁻¹::AbstractVector{<:Number}, isbloch::Bool, e⁻ⁱᵏᴸ::Number=1.0; α::Number=1.0) where {T,K,OP}
+    size(Gv) == size(Fu) || throw(ArgumentError("size(Gv) != size(Fu)"))
+    keep, ptrs, cc = coefs((∆w⁻¹,))
+    N = Int64[size(Fu)...]
+    GC.@preserve keep check(ccall((:sgc_apply_partial, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+        Gv.ptr, Fu.ptr, opcode(Val(OP)), dtype_code(T), K, N, nw, isfwd, ptrs[1], cc, isbloch, pair(e⁻ⁱᵏᴸ), pair(α), C_NULL))
+    return nothing
+end
+
+# apply_m̂!  — src/matrixfree/mean.jl:102/295/432 (arithmetic), :493/705/856 (weighted)
+function apply_m̂!(Gv::DeviceArray{T,K}, Fu::DeviceArray{T,K}, ::Val{OP}, nw::Integer, isfwd::Bool, isbloch::Bool,
+                  e⁻ⁱᵏᴸ::Number=1.0; α::Number=1.0) where {T,K,OP}
+    N = Int64[size(Fu)...]
+    check(ccall((:sgc_apply_mhat, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+        Gv.ptr, Fu.ptr, opcode(Val(OP)), dtype_code(T), K, N, nw, isfwd, C_NULL, C_NULL, 0, isbloch, pair(e⁻ⁱᵏᴸ), pair(α), C_NULL))
+    return nothing
+end
+
+function apply_m̂!(Gv::DeviceArray{T,K}, Fu::DeviceArray{T,K}, ::Val{OP}, nw::Integer, isfwd::Bool,
+                  ∆w::AbstractVector{<:Number}, ∆w′⁻¹::AbstractVector{<:Number}, isbloch::Bool, e⁻ⁱᵏᴸ::Number=1.0;
+                  α::Number=1.0) where {T,K,OP}
+    keep, ptrs, cc = coefs((∆w, ∆w′⁻¹))
+    N = Int64[size(Fu)...]
+    GC.@preserve keep check(ccall((:sgc_apply_mhat, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+        Gv.ptr, Fu.ptr, opcode(Val(OP)), dtype_code(T), K, N, nw, isfwd, ptrs[1], ptrs[2], cc, isbloch, pair(e⁻ⁱᵏᴸ), pair(α), C_NULL))
+    return nothing
+end
+
+# apply_curl!  — src/matrixfree/differential/curl.jl:52-63 (concrete method; the wrappers :12-49
+# convert to SVec and land here).  ONE fused kernel for the full 3-D curl.
+function apply_curl!(G::DeviceArray{T,K₊₁}, F::DeviceArray{T,K₊₁}, ::Val{OP}, isfwd, ∆l⁻¹::NTuple{K,AbstractVector{<:Number}},
+                     isbloch, e⁻ⁱᵏᴸ; cmp_shp=1:K, cmp_out=1:size(G, K₊₁), cmp_in=1:size(F, K₊₁), α::Number=1.0) where {T,K,K₊₁,OP}
+    K₊₁ == K + 1 || throw(ArgumentError("K₊₁ != K+1"))
+    keep, ptrs, cc = coefs(∆l⁻¹)
+    N = Int64[size(G)[1:K]...]
+    GC.@preserve keep check(ccall((:sgc_apply_curl, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble},
+         Ptr{Cint}, Cint, Ptr{Cint}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cvoid}),
+        G.ptr, F.ptr, opcode(Val(OP)), dtype_code(T), K, N, cints(isfwd), ptrs, cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ),
+        cints(cmp_shp), length(cmp_out), cints(cmp_out), length(cmp_in), cints(cmp_in), pair(α), C_NULL))
+    return nothing
+end
+
+# apply_divg! / apply_grad!  — src/matrixfree/differential/divergence.jl:41-49, gradient.jl:41-49
+for (fn, sym) in ((:apply_divg!, :sgc_apply_divg), (:apply_grad!, :sgc_apply_grad))
+    @eval function $fn(A::DeviceArray{T}, B::DeviceArray{T}, ::Val{OP}, isfwd, ∆l⁻¹::NTuple{K,AbstractVector{<:Number}},
+                       isbloch, e⁻ⁱᵏᴸ; α::Number=1.0) where {T,K,OP}
+        keep, ptrs, cc = coefs(∆l⁻¹)
+        N = Int64[length.(∆l⁻¹)...]
+        GC.@preserve keep check(ccall(($(QuoteNode(sym)), LIB), Cint,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+            A.ptr, B.ptr, opcode(Val(OP)), dtype_code(T), K, N, cints(isfwd), ptrs, cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ), pair(α), C_NULL))
+        return nothing
+    end
+end
+
+# apply_mean!  — src/matrixfree/mean.jl:47-54 (arithmetic), :69-78 (weighted)
+function apply_mean!(G::DeviceArray{T}, F::DeviceArray{T}, ::Val{OP}, isfwd, isbloch, e⁻ⁱᵏᴸ; α::Number=1.0) where {T,OP}
+    K = length(isfwd)
+    N = Int64[size(G)[1:K]...]
+    check(ccall((:sgc_apply_mean, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+        G.ptr, F.ptr, opcode(Val(OP)), dtype_code(T), K, N, cints(isfwd), C_NULL, C_NULL, 0, cints(isbloch), pairs(e⁻ⁱᵏᴸ), pair(α), C_NULL))
+    return nothing
+end
+
+function apply_mean!(G::DeviceArray{T}, F::DeviceArray{T}, ::Val{OP}, isfwd, ∆l::NTuple{K,AbstractVector{<:Number}},
+                     ∆l′⁻¹::NTuple{K,AbstractVector{<:Number}}, isbloch, e⁻ⁱᵏᴸ; α::Number=1.0) where {T,K,OP}
+    keep, ptrs, cc = coefs((∆l..., ∆l′⁻¹...))
+    N = Int64[length.(∆l)...]
+    GC.@preserve keep check(ccall((:sgc_apply_mean, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cvoid}),
+        G.ptr, F.ptr, opcode(Val(OP)), dtype_code(T), K, N, cints(isfwd), ptrs[1:K], ptrs[K+1:2K], cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ), pair(α), C_NULL))
+    return nothing
+end
+
+# ---------------------------------------------------------------------------------------------
+# sparse assembly: handle → shape → colptr (count + scan) → fill → SparseMatrixCSC
+# ---------------------------------------------------------------------------------------------
+function finish_csc(h::Ptr{Cvoid})
+    try
+        m, n, vt = Ref{Int64}(0), Ref{Int64}(0), Ref{Cint}(0)
+        check(ccall((:sgc_asm_shape, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Cint}), h, m, n, vt))
+        Tv = vt[] == SGC_C128 ? ComplexF64 : Float64
+        nnz = Ref{Int64}(0)
+        check(ccall((:sgc_asm_nnz_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), h, nnz))
+        colptr, rowval, nzval = Vector{Int64}(undef, n[] + 1), Vector{Int64}(undef, nnz[]), Vector{Tv}(undef, nnz[])
+        check(ccall((:sgc_asm_fill_host, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Cint, Ptr{Int64}, Ptr{Cvoid}),
+                    h, colptr, 1, rowval, nzval))
+        return SparseMatrixCSC{Tv,Int64}(m[], n[], colptr, rowval, nzval)  # 1-based arrays, used as they are
+    finally
+        ccall((:sgc_asm_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+    end
+end
+
+ecomplex(e) = Cint(eltype(e) <: Complex)
+
+# create_∂  — src/matrix/differential/partial.jl:54-60
+function create_∂(::Val{:b200}, nw::Integer, isfwd::Bool, N::AbstractVector{<:Integer}, ∆w⁻¹::AbstractVector{<:Number},
+                  isbloch::Bool=true, e⁻ⁱᵏᴸ::Number=1.0)
+    keep, ptrs, cc = coefs((∆w⁻¹,))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:sgc_asm_create_partial, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint),
+        h, length(N), Int64[N...], nw, isfwd, ptrs[1], cc, isbloch, pair(e⁻ⁱᵏᴸ), ecomplex(e⁻ⁱᵏᴸ)))
+    return finish_csc(h[])
+end
+
+# create_m̂  — src/matrix/mean.jl:131-138
+function create_m̂(::Val{:b200}, nw::Integer, isfwd::Bool, N::AbstractVector{<:Integer}, ∆w::AbstractVector{<:Number},
+                  ∆w′⁻¹::AbstractVector{<:Number}, isbloch::Bool=true, e⁻ⁱᵏᴸ::Number=1.0)
+    keep, ptrs, cc = coefs((∆w, ∆w′⁻¹))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:sgc_asm_create_mhat, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Cint),
+        h, length(N), Int64[N...], nw, isfwd, ptrs[1], ptrs[2], cc, isbloch, pair(e⁻ⁱᵏᴸ), ecomplex(e⁻ⁱᵏᴸ)))
+    return finish_csc(h[])
+end
+
+# create_curl  — src/matrix/differential/curl.jl:50-58
+function create_curl(::Val{:b200}, isfwd, ∆l⁻¹::NTuple{K,AbstractVector{<:Number}}, isbloch, e⁻ⁱᵏᴸ;
+                     cmp_shp=1:K, cmp_out=1:K, cmp_in=1:K, order_cmpfirst::Bool=true) where {K}
+    keep, ptrs, cc = coefs(∆l⁻¹)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:sgc_asm_create_curl, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Cint, Ptr{Cint}, Cint,
+         Ptr{Cint}, Cint, Ptr{Cint}, Cint),
+        h, K, Int64[length.(∆l⁻¹)...], cints(isfwd), ptrs, cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ), ecomplex(e⁻ⁱᵏᴸ), cints(cmp_shp),
+        length(cmp_out), cints(cmp_out), length(cmp_in), cints(cmp_in), order_cmpfirst))
+    return finish_csc(h[])
+end
+
+# create_divg / create_grad  — src/matrix/differential/divergence.jl:37-42, gradient.jl:37-42
+for (fn, sym) in ((:create_divg, :sgc_asm_create_divg), (:create_grad, :sgc_asm_create_grad))
+    @eval function $fn(::Val{:b200}, isfwd, ∆l⁻¹::NTuple{K,AbstractVector{<:Number}}, isbloch, e⁻ⁱᵏᴸ;
+                       order_cmpfirst::Bool=true) where {K}
+        keep, ptrs, cc = coefs(∆l⁻¹)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve keep check(ccall(($(QuoteNode(sym)), LIB), Cint,
+            (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint),
+            h, K, Int64[length.(∆l⁻¹)...], cints(isfwd), ptrs, cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ), ecomplex(e⁻ⁱᵏᴸ), order_cmpfirst))
+        return finish_csc(h[])
+    end
+end
+
+# create_mean  — src/matrix/mean.jl:72-78
+function create_mean(::Val{:b200}, isfwd, ∆l::NTuple{K,AbstractVector{<:Number}}, ∆l′⁻¹::NTuple{K,AbstractVector{<:Number}},
+                     isbloch, e⁻ⁱᵏᴸ; order_cmpfirst::Bool=true) where {K}
+    keep, ptrs, cc = coefs((∆l..., ∆l′⁻¹...))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve keep check(ccall((:sgc_asm_create_mean, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Cint, Cint),
+        h, K, Int64[length.(∆l)...], cints(isfwd), ptrs[1:K], ptrs[K+1:2K], cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ), ecomplex(e⁻ⁱᵏᴸ),
+        order_cmpfirst))
+    return finish_csc(h[])
+end
+
+# create_πcmp  — src/matrix/permutation.jl:15-19
+function create_πcmp(::Val{:b200}, N::AbstractVector{<:Integer}, permute::AbstractVector{<:Integer};
+                     scale::AbstractVector{<:Number}=ones(length(permute)), order_cmpfirst::Bool=true)
+    Ts = eltype(scale) <: Complex ? ComplexF64 : Float64
+    sc = Vector{Ts}(scale)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve sc check(ccall((:sgc_asm_create_picmp, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Ptr{Int64}, Cint, Ptr{Cint}, Ptr{Cvoid}, Cint, Cint),
+        h, length(N), Int64[N...], length(permute), cints(permute), sc, Ts == ComplexF64, order_cmpfirst))
+    return finish_csc(h[])
+end
+
+end # module SGCB200
