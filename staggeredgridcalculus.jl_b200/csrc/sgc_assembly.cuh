@@ -9,9 +9,10 @@
 //
 //   column → its ≤ 2·Kout candidate triplets (the same triplets the reference emits for that
 //   column, duplicates summed in the reference's order, value==0 dropped) → count
-//   → device-wide exclusive prefix scan (colptr) → the triplets are sorted by row inside the
-//   column segment (a register sorting network: the segmented sort of a ≤ 6-element segment)
-//   → staged in shared memory → written to rowval / nzval with fully coalesced stores.
+//   → prefix scan (per CTA in-kernel, across CTAs a device scan of the CTA totals) = colptr
+//   → the triplets are sorted by row inside the column segment (a register sorting network:
+//   the segmented sort of a ≤ 6-element segment) → staged in shared memory → written to
+//   rowval / nzval with fully coalesced stores.
 //
 // Index arithmetic is 64-bit throughout (512³ curl has 1.6e9 nonzeros).
 #pragma once
@@ -42,28 +43,15 @@ struct AsmParams {
     int64_t ncol;                 // Kin*M
     int64_t row_begin, row_end;   // global rows kept (0-based, half-open)
     int64_t index_base;
+    // cell-major kernels: the blocks of each block column, and the group geometry
+    int nblk_of[3];
+    int blk_of[3][3];
+    int cols_per_group;           // Kin for component-major ordering (a group = one grid cell), else 1
+    int64_t ngroups;              // M (component-major) or Kin*M (block ordering: group = (nu, cell))
 };
 
 SGC_D bool is_zero(double v) { return v == 0.0; }
 SGC_D bool is_zero(cplx v) { return v.re == 0.0 && v.im == 0.0; }
-
-// Subscripts of grid cell c and the block column of matrix column `col`.
-template <typename T, typename IDX>
-SGC_D void column_decode(const AsmParams<T> &p, int64_t col, int &nu, IDX &c, IDX sub[3]) {
-    if (p.cmpfirst) {
-        const IDX kin = (IDX)p.Kin;
-        c = kin == 3 ? (IDX)col / 3 : (kin == 2 ? (IDX)col / 2 : (IDX)col);
-        nu = (int)((IDX)col - c * kin);
-    } else {
-        nu = (int)((IDX)col / (IDX)p.M);
-        c = (IDX)col - (IDX)nu * (IDX)p.M;
-    }
-    const IDX n0 = (IDX)p.N[0], n1 = (IDX)p.N[1];
-    const IDX t = c / n0;
-    sub[0] = c - t * n0;
-    sub[2] = t / n1;
-    sub[1] = t - sub[2] * n1;
-}
 
 // The (≤ 2) triplets block B contributes to the column of grid cell c: value, LOCAL row of the
 // (block of the) matrix, and validity (nonzero value, row inside the partition).
@@ -102,25 +90,6 @@ SGC_D void block_entries(const AsmParams<T> &p, const AsmBlock<T> &B, IDX c, con
     }
 }
 
-// Number of stored entries of one column.
-template <typename T, typename IDX>
-SGC_D int column_count(const AsmParams<T> &p, int64_t col) {
-    int nu;
-    IDX c, sub[3];
-    column_decode<T, IDX>(p, col, nu, c, sub);
-    int cnt = 0;
-    for (int b = 0; b < p.nblk; ++b) {
-        const AsmBlock<T> &B = p.blk[b];
-        if (B.nu != nu) continue;
-        T v[2];
-        int64_t r[2];
-        bool ok[2];
-        block_entries<T, IDX>(p, B, c, sub, v, r, ok);
-        cnt += (int)ok[0] + (int)ok[1];
-    }
-    return cnt;
-}
-
 template <typename T>
 SGC_D void cmpswap(int64_t &ra, T &va, int64_t &rb, T &vb) {
     if (rb < ra) {
@@ -129,36 +98,76 @@ SGC_D void cmpswap(int64_t &ra, T &va, int64_t &rb, T &vb) {
     }
 }
 
-// The entries of one column sorted by row, in registers: invalid slots carry row = INT64_MAX and
-// sink to the end of a fixed 6-input sorting network (the "segmented sort" of a ≤ 6-entry
-// column segment).  Returns the count.
+// ---------------------------------------------------------------------------------------------
+// Cell-major assembly kernels (the fast path)
+// ---------------------------------------------------------------------------------------------
+// A "group" is the set of matrix columns one thread owns.  With the default component-major
+// ordering (order_cmpfirst = true) the Kin columns of a grid cell are consecutive, so a group is
+// a cell and a CTA's output is one contiguous range of colptr / rowval / nzval; with block
+// ordering a group is a single column (nu, cell).  All threads of a warp then walk the same
+// blocks (no divergence), subscripts come from two 32-bit divisions per thread, and the tables
+// V₀/Vₛ are read with lane-contiguous or warp-uniform indices.
+//
+//   pass 1  k_asm_group<COUNT>  : per-CTA entry totals (nothing else is written)
+//           cub::DeviceScan over the CTA totals (≤ a few MB)
+//   pass 2  k_asm_group<FILL…>  : per-thread counts → block scan → colptr, and the sorted entries
+//                                 staged in shared memory → coalesced rowval / nzval stores.
+// HBM traffic is the algorithmic minimum: colptr, rowval, nzval are each written once and nothing
+// of size O(nnz) is ever read.
+enum : int { ASM_COUNT = 0, ASM_COLPTR = 1, ASM_FILL = 2, ASM_FILL_ALL = 3 };
+
 template <typename T, typename IDX>
-SGC_D int column_entries(const AsmParams<T> &p, int64_t col, int64_t (&rows)[ASM_MAX_ENTRIES], T (&vals)[ASM_MAX_ENTRIES]) {
-    int nu;
-    IDX c, sub[3];
-    column_decode<T, IDX>(p, col, nu, c, sub);
+SGC_D void group_decode(const AsmParams<T> &p, int64_t g, int &nu0, IDX &c, IDX sub[3]) {
+    if (p.cols_per_group > 1 || p.Kin == 1) {
+        nu0 = 0;
+        c = (IDX)g;
+    } else {  // block ordering: g = nu*M + c, no division needed
+        nu0 = (g >= 2 * p.M) ? 2 : (g >= p.M ? 1 : 0);
+        c = (IDX)(g - (int64_t)nu0 * p.M);
+    }
+    const IDX n0 = (IDX)p.N[0], n1 = (IDX)p.N[1];
+    const IDX t = c / n0;
+    sub[0] = c - t * n0;
+    sub[2] = t / n1;
+    sub[1] = t - sub[2] * n1;
+}
+
+template <typename T, typename IDX>
+SGC_D int column_count_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3]) {
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (q < p.nblk_of[nu]) {
+            T v[2];
+            int64_t r[2];
+            bool ok[2];
+            block_entries<T, IDX>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
+            cnt += (int)ok[0] + (int)ok[1];
+        }
+    }
+    return cnt;
+}
+
+// sorted entries of column (nu, c) in registers; returns the count
+template <typename T, typename IDX>
+SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3], int64_t (&rows)[ASM_MAX_ENTRIES],
+                            T (&vals)[ASM_MAX_ENTRIES]) {
     constexpr int64_t INVALID = 0x7fffffffffffffffLL;
 #pragma unroll
     for (int q = 0; q < ASM_MAX_ENTRIES; ++q) { rows[q] = INVALID; vals[q] = zero_of(T{}); }
-    int cnt = 0, slot = 0;  // slot: which pair of the register array the next matching block fills
-    for (int b = 0; b < p.nblk; ++b) {
-        const AsmBlock<T> &B = p.blk[b];
-        if (B.nu != nu) continue;
-        T v[2];
-        int64_t r[2];
-        bool ok[2];
-        block_entries<T, IDX>(p, B, c, sub, v, r, ok);
-        cnt += (int)ok[0] + (int)ok[1];
-        // static register indexing: the block-column has at most 3 blocks
+    int cnt = 0;
 #pragma unroll
-        for (int s3 = 0; s3 < 3; ++s3)
-            if (slot == s3) {
-                if (ok[0]) { rows[2 * s3] = r[0]; vals[2 * s3] = v[0]; }
-                if (ok[1]) { rows[2 * s3 + 1] = r[1]; vals[2 * s3 + 1] = v[1]; }
-            }
-        ++slot;
+    for (int q = 0; q < 3; ++q) {
+        if (q < p.nblk_of[nu]) {
+            T v[2];
+            int64_t r[2];
+            bool ok[2];
+            block_entries<T, IDX>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
+            cnt += (int)ok[0] + (int)ok[1];
+            if (ok[0]) { rows[2 * q] = r[0]; vals[2 * q] = v[0]; }
+            if (ok[1]) { rows[2 * q + 1] = r[1]; vals[2 * q + 1] = v[1]; }
+        }
     }
-    // 6-input sorting network (12 compare-exchanges)
     cmpswap(rows[0], vals[0], rows[5], vals[5]); cmpswap(rows[1], vals[1], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[4], vals[4]);
     cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
     cmpswap(rows[0], vals[0], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[5], vals[5]);
@@ -167,48 +176,95 @@ SGC_D int column_entries(const AsmParams<T> &p, int64_t col, int64_t (&rows)[ASM
     return cnt;
 }
 
-// Functor for the scan's input iterator: number of stored entries of column `col`
-// (0 for the one-past-the-end column so that the scan also produces colptr[n]).
-template <typename T, typename IDX>
-struct ColumnCount {
-    AsmParams<T> p;
-    __device__ int64_t operator()(int64_t col) const {
-        if (col >= p.ncol) return 0;
-        return (int64_t)column_count<T, IDX>(p, col);
-    }
-};
-
-// Fill: one thread per column, entries staged through shared memory so that the global
-// stores of rowval / nzval are contiguous per CTA.
-template <typename T, typename IDX, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_asm_fill(const __grid_constant__ AsmParams<T> p,
-                                                    const int64_t *__restrict__ colptr,
-                                                    int64_t *__restrict__ rowval, T *__restrict__ nzval,
-                                                    int max_per_col) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T *s_vals = reinterpret_cast<T *>(smem_raw);
-    int64_t *s_rows = reinterpret_cast<int64_t *>(smem_raw + sizeof(T) * (size_t)BLOCK * max_per_col);
-
-    const int64_t col0 = (int64_t)blockIdx.x * BLOCK;
-    const int64_t col = col0 + threadIdx.x;
-    const int64_t col_end = min(col0 + (int64_t)BLOCK, p.ncol);
-    const int64_t base = colptr[col0] - p.index_base;
-    const int64_t total = colptr[col_end] - p.index_base - base;
-
-    if (col < p.ncol) {
-        int64_t rows[ASM_MAX_ENTRIES];
-        T vals[ASM_MAX_ENTRIES];
-        const int cnt = column_entries<T, IDX>(p, col, rows, vals);
-        const int64_t off = colptr[col] - p.index_base - base;
+// block-wide exclusive scan of one int per thread (BLOCK ≤ 1024, power of two multiple of 32)
+template <int BLOCK>
+SGC_D int block_exclusive_scan(int v, int *s_warp, int &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = v;
 #pragma unroll
-        for (int q = 0; q < ASM_MAX_ENTRIES; ++q)
-            if (q < cnt) {
-                s_rows[off + q] = rows[q] + p.index_base;
-                s_vals[off + q] = vals[q];
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = (lane < BLOCK / 32) ? s_warp[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, w, d);
+            if (lane >= d) w += n;
+        }
+        s_warp[32 + lane] = w;  // inclusive warp prefix
+    }
+    __syncthreads();
+    total = s_warp[32 + BLOCK / 32 - 1];
+    return incl - v + (wid ? s_warp[32 + wid - 1] : 0);
+}
+
+template <typename T, typename IDX, int BLOCK, int MODE>
+__global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ AsmParams<T> p,
+                                                     int64_t *__restrict__ cta_total,        // COUNT: out
+                                                     const int64_t *__restrict__ cta_offset,  // COLPTR / FILL_ALL: in
+                                                     const int64_t *__restrict__ colptr_in,   // FILL: in
+                                                     int64_t *__restrict__ colptr_out,        // COLPTR / FILL_ALL: out
+                                                     int64_t *__restrict__ rowval, T *__restrict__ nzval, int max_per_group) {
+    __shared__ int s_warp[64];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int64_t g0 = (int64_t)blockIdx.x * BLOCK;
+    const int64_t g = g0 + threadIdx.x;
+    const bool live = g < p.ngroups;
+    int nu0 = 0;
+    IDX c = 0, sub[3] = {0, 0, 0};
+    if (live) group_decode<T, IDX>(p, g, nu0, c, sub);
+    const int ncols = p.cols_per_group;
+
+    // per-column counts of my group
+    int cnt[3] = {0, 0, 0};
+    int mine = 0;
+    if (live) {
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < ncols) { cnt[q] = column_count_of<T, IDX>(p, nu0 + q, c, sub); mine += cnt[q]; }
+    }
+    int total;
+    const int off0 = block_exclusive_scan<BLOCK>(mine, s_warp, total);
+    if (MODE == ASM_COUNT) {
+        if (threadIdx.x == 0) cta_total[blockIdx.x] = total;
+        return;
+    }
+    // absolute (0-based) position of this CTA's first entry
+    const int64_t col0 = g0 * ncols;
+    const int64_t base = (MODE == ASM_FILL) ? colptr_in[col0] - p.index_base : cta_offset[blockIdx.x];
+    if (MODE == ASM_COLPTR || MODE == ASM_FILL_ALL) {
+        if (live) {
+            int64_t o = base + off0 + p.index_base;
+            const int64_t col = g * ncols;
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < ncols) { colptr_out[col + q] = o; o += cnt[q]; }
+            if (g == p.ngroups - 1) colptr_out[p.ncol] = o;  // one-past-the-end entry
+        }
+        if (MODE == ASM_COLPTR) return;
+    }
+    T *s_vals = reinterpret_cast<T *>(smem_raw);
+    int64_t *s_rows = reinterpret_cast<int64_t *>(smem_raw + sizeof(T) * (size_t)BLOCK * max_per_group);
+    if (live) {
+        int o = off0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+            if (q < ncols) {
+                int64_t rows[ASM_MAX_ENTRIES];
+                T vals[ASM_MAX_ENTRIES];
+                column_entries_of<T, IDX>(p, nu0 + q, c, sub, rows, vals);
+#pragma unroll
+                for (int e = 0; e < ASM_MAX_ENTRIES; ++e)
+                    if (e < cnt[q]) { s_rows[o + e] = rows[e] + p.index_base; s_vals[o + e] = vals[e]; }
+                o += cnt[q];
             }
     }
     __syncthreads();
-    for (int64_t q = threadIdx.x; q < total; q += BLOCK) {
+    for (int q = threadIdx.x; q < total; q += BLOCK) {
         rowval[base + q] = s_rows[q];
         stg_stream(nzval + base + q, s_vals[q]);
     }

@@ -83,6 +83,9 @@ struct sgc_asm {
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;
     int64_t nnz = -1;
+    int64_t *cta_total = nullptr, *cta_offset = nullptr;  // per-CTA entry counts and their exclusive scan
+    int64_t ncta = 0;
+    bool counted = false;
     // host convenience
     int64_t *d_colptr = nullptr;
 };

@@ -7,8 +7,6 @@
 #include "sgc_internal.h"
 
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/counting_input_iterator.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "sgc_assembly.cuh"
 #include "sgc_kernels.cuh"
@@ -718,6 +716,8 @@ extern "C" int sgc_asm_destroy(sgc_asm *a) {
     if (a->arena) cudaFree(a->arena);
     if (a->scan_tmp) cudaFree(a->scan_tmp);
     if (a->d_colptr) cudaFree(a->d_colptr);
+    if (a->cta_total) cudaFree(a->cta_total);
+    if (a->cta_offset) cudaFree(a->cta_offset);
     delete a;
     return SGC_OK;
 }
@@ -933,6 +933,7 @@ extern "C" int sgc_asm_set_row_range(sgc_asm *a, int64_t row_begin, int64_t row_
     a->row_begin = row_begin;
     a->row_end = row_end;
     a->nnz = -1;
+    a->counted = false;
     return SGC_OK;
 }
 
@@ -960,95 +961,141 @@ static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
     p.ncol = (int64_t)a->Kin * a->M;
     p.row_begin = a->row_begin; p.row_end = a->row_end;
     p.index_base = index_base;
+    for (int nu = 0; nu < 3; ++nu) p.nblk_of[nu] = 0;
+    for (int b = 0; b < p.nblk; ++b) {
+        const int nu = a->blocks[b].nu;
+        if (p.nblk_of[nu] < 3) p.blk_of[nu][p.nblk_of[nu]] = b;
+        p.nblk_of[nu]++;
+    }
+    p.cols_per_group = a->cmpfirst ? a->Kin : 1;
+    p.ngroups = a->cmpfirst ? a->M : (int64_t)a->Kin * a->M;
     return p;
 }
 
-template <typename T, typename IDX>
-static int asm_colptr_typed(sgc_asm *a, int64_t *colptr, int index_base, cudaStream_t st) {
+constexpr int ASM_BLOCK = 128;
+
+static int asm_max_per_group(const sgc_asm *a) {
+    int per_nu[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
+    for (auto &B : a->blocks) { per_nu[B.nu] += (B.ns == 0 ? 1 : 2); nb[B.nu]++; }
+    for (int nu = 0; nu < 3; ++nu)
+        if (nb[nu] > 3 || per_nu[nu] > ASM_MAX_ENTRIES) return -1;
+    if (a->cmpfirst) return std::max(1, per_nu[0] + per_nu[1] + per_nu[2]);
+    return std::max(1, std::max(per_nu[0], std::max(per_nu[1], per_nu[2])));
+}
+
+template <typename T, typename IDX, int MODE>
+static int asm_launch(const sgc_asm *a, int index_base, const int64_t *colptr_in, int64_t *colptr_out, int64_t *rowval,
+                      T *nzval, cudaStream_t st) {
     AsmParams<T> p = asm_params<T>(a, index_base);
-    ColumnCount<T, IDX> f{p};
-    cub::CountingInputIterator<int64_t> cnt(0);
-    cub::TransformInputIterator<int64_t, ColumnCount<T, IDX>, cub::CountingInputIterator<int64_t>> in(cnt, f);
+    const int maxg = asm_max_per_group(a);
+    if (maxg < 0) return fail(SGC_ERR_INVALID, "operator has more than %d entries per column", ASM_MAX_ENTRIES);
+    if (a->ncta == 0) return SGC_OK;
+    const bool needs_smem = (MODE == ASM_FILL || MODE == ASM_FILL_ALL);
+    const size_t smem = needs_smem ? (sizeof(T) + sizeof(int64_t)) * (size_t)ASM_BLOCK * maxg : 0;
+    auto kern = k_asm_group<T, IDX, ASM_BLOCK, MODE>;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)a->ncta, ASM_BLOCK, smem, st>>>(p, a->cta_total, a->cta_offset, colptr_in, colptr_out, rowval, nzval, maxg);
+    return check_launch("k_asm_group");
+}
+
+template <int MODE>
+static int asm_dispatch(const sgc_asm *a, int index_base, const int64_t *colptr_in, int64_t *colptr_out, int64_t *rowval,
+                        void *nzval, cudaStream_t st) {
+    const int64_t ncol = (int64_t)a->Kin * a->M;
+    const bool small = ncol < (int64_t)0xffffffffLL && a->M < (int64_t)0xffffffffLL;
+    if (a->cx) return small ? asm_launch<cplx, uint32_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (cplx *)nzval, st)
+                            : asm_launch<cplx, uint64_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (cplx *)nzval, st);
+    return small ? asm_launch<double, uint32_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (double *)nzval, st)
+                 : asm_launch<double, uint64_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (double *)nzval, st);
+}
+
+// pass 1: per-CTA totals + their exclusive scan; leaves nnz in the handle (synchronises)
+static int asm_count(sgc_asm *a, cudaStream_t st) {
+    if (a->counted) return SGC_OK;
+    REQUIRE(a->blocks.size() <= (size_t)ASM_MAX_BLOCKS, "too many blocks");
+    const int64_t ngroups = a->cmpfirst ? a->M : (int64_t)a->Kin * a->M;
+    const int64_t ncta = (ngroups + ASM_BLOCK - 1) / ASM_BLOCK;
+    REQUIRE(ncta < (int64_t)0x7fffffff, "matrix too large for one launch");
+    if (ncta != a->ncta || !a->cta_total) {
+        if (a->cta_total) cudaFree(a->cta_total);
+        if (a->cta_offset) cudaFree(a->cta_offset);
+        a->cta_total = a->cta_offset = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&a->cta_total, sizeof(int64_t) * (size_t)(ncta + 1)));
+        CUDA_TRY(cudaMalloc((void **)&a->cta_offset, sizeof(int64_t) * (size_t)(ncta + 1)));
+        a->ncta = ncta;
+    }
+    int s = asm_dispatch<ASM_COUNT>(a, 0, nullptr, nullptr, nullptr, nullptr, st);
+    if (s) return s;
+    CUDA_TRY(cudaMemsetAsync(a->cta_total + ncta, 0, sizeof(int64_t), st));
     size_t need = 0;
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(nullptr, need, in, colptr, cub::Sum(), (int64_t)index_base, p.ncol + 1, st));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, a->cta_total, a->cta_offset, (int)(ncta + 1), st));
     if (need > a->scan_tmp_bytes) {
         if (a->scan_tmp) cudaFree(a->scan_tmp);
         a->scan_tmp = nullptr;
         CUDA_TRY(cudaMalloc(&a->scan_tmp, need));
         a->scan_tmp_bytes = need;
     }
-    CUDA_TRY(cub::DeviceScan::ExclusiveScan(a->scan_tmp, need, in, colptr, cub::Sum(), (int64_t)index_base, p.ncol + 1, st));
-    g_launches.fetch_add(2, std::memory_order_relaxed);  // DeviceScan: init + scan kernels
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(a->scan_tmp, need, a->cta_total, a->cta_offset, (int)(ncta + 1), st));
+    sgc_count_launches(2);
+    int64_t total = 0;
+    CUDA_TRY(cudaMemcpyAsync(&total, a->cta_offset + ncta, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    a->nnz = total;
+    a->counted = true;
     return SGC_OK;
+}
+
+extern "C" int sgc_asm_count(sgc_asm *a, int64_t *nnz, void *stream) {
+    REQUIRE(a, "handle is NULL");
+    int s = asm_count(a, (cudaStream_t)stream);
+    if (s) return s;
+    if (nnz) *nnz = a->nnz;
+    return SGC_OK;
+}
+
+extern "C" int sgc_asm_fill_all(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval, void *stream) {
+    REQUIRE(a && colptr, "NULL argument");
+    REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+    int s = asm_count(a, (cudaStream_t)stream);
+    if (s) return s;
+    REQUIRE(a->nnz == 0 || (rowval && nzval), "rowval / nzval are NULL");
+    if (a->ncta == 0) {  // empty matrix: colptr[0] only
+        int64_t b = index_base;
+        CUDA_TRY(cudaMemcpyAsync(colptr, &b, sizeof b, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+        return SGC_OK;
+    }
+    return asm_dispatch<ASM_FILL_ALL>(a, index_base, nullptr, colptr, rowval, nzval, (cudaStream_t)stream);
 }
 
 extern "C" int sgc_asm_colptr(sgc_asm *a, int64_t *colptr, int index_base, int64_t *nnz, void *stream) {
     REQUIRE(a && colptr, "NULL argument");
     REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
-    REQUIRE(a->blocks.size() <= (size_t)ASM_MAX_BLOCKS, "too many blocks");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t ncol = (int64_t)a->Kin * a->M;
-    const bool small = ncol < (int64_t)0xffffffffLL && a->M < (int64_t)0xffffffffLL;
-    int s;
-    if (a->cx) s = small ? asm_colptr_typed<cplx, uint32_t>(a, colptr, index_base, st)
-                         : asm_colptr_typed<cplx, uint64_t>(a, colptr, index_base, st);
-    else s = small ? asm_colptr_typed<double, uint32_t>(a, colptr, index_base, st)
-                   : asm_colptr_typed<double, uint64_t>(a, colptr, index_base, st);
+    int s = asm_count(a, (cudaStream_t)stream);
     if (s) return s;
-    int64_t last = 0;
-    CUDA_TRY(cudaMemcpyAsync(&last, colptr + ncol, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    a->nnz = last - index_base;
     if (nnz) *nnz = a->nnz;
-    return SGC_OK;
-}
-
-template <typename T, typename IDX>
-static int asm_fill_typed(const sgc_asm *a, const int64_t *colptr, int index_base, int64_t *rowval, T *nzval,
-                          cudaStream_t st) {
-    AsmParams<T> p = asm_params<T>(a, index_base);
-    // maximum number of entries one column can hold: 2 per block in its block column
-    int per_nu[3] = {0, 0, 0};
-    for (auto &B : a->blocks) per_nu[B.nu] += (B.ns == 0 ? 1 : 2);
-    int maxe = std::max(per_nu[0], std::max(per_nu[1], per_nu[2]));
-    if (maxe < 1) maxe = 1;
-    if (maxe > ASM_MAX_ENTRIES) return fail(SGC_ERR_INVALID, "operator has more than %d entries per column", ASM_MAX_ENTRIES);
-    constexpr int BLOCK = 256;
-    const size_t smem = (sizeof(T) + sizeof(int64_t)) * (size_t)BLOCK * maxe;
-    const int64_t blocks = (p.ncol + BLOCK - 1) / BLOCK;
-    if (blocks == 0) return SGC_OK;
-    k_asm_fill<T, IDX, BLOCK><<<(unsigned)blocks, BLOCK, smem, st>>>(p, colptr, rowval, nzval, maxe);
-    return check_launch("k_asm_fill");
+    return asm_dispatch<ASM_COLPTR>(a, index_base, nullptr, colptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int sgc_asm_fill(const sgc_asm *a, const int64_t *colptr, int index_base, int64_t *rowval,
                             void *nzval, void *stream) {
     REQUIRE(a && colptr, "NULL argument");
     REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t ncol = (int64_t)a->Kin * a->M;
-    REQUIRE(ncol / 256 + 1 < (int64_t)0x7fffffff, "matrix too large for one launch");
-    const bool small = ncol < (int64_t)0xffffffffLL && a->M < (int64_t)0xffffffffLL;
-    if (a->cx) return small ? asm_fill_typed<cplx, uint32_t>(a, colptr, index_base, rowval, (cplx *)nzval, st)
-                            : asm_fill_typed<cplx, uint64_t>(a, colptr, index_base, rowval, (cplx *)nzval, st);
-    return small ? asm_fill_typed<double, uint32_t>(a, colptr, index_base, rowval, (double *)nzval, st)
-                 : asm_fill_typed<double, uint64_t>(a, colptr, index_base, rowval, (double *)nzval, st);
+    REQUIRE(a->counted, "call sgc_asm_colptr (or sgc_asm_count) before sgc_asm_fill");
+    return asm_dispatch<ASM_FILL>(a, index_base, colptr, nullptr, rowval, nzval, (cudaStream_t)stream);
 }
 
 extern "C" int sgc_asm_nnz_host(sgc_asm *a, int64_t *nnz) {
     REQUIRE(a && nnz, "NULL argument");
-    const int64_t ncol = (int64_t)a->Kin * a->M;
-    if (!a->d_colptr) CUDA_TRY(cudaMalloc((void **)&a->d_colptr, sizeof(int64_t) * (size_t)(ncol + 1)));
-    return sgc_asm_colptr(a, a->d_colptr, 1, nnz, nullptr);
+    return sgc_asm_count(a, nnz, nullptr);
 }
 
 extern "C" int sgc_asm_fill_host(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval) {
     REQUIRE(a && colptr, "NULL argument");
     const int64_t ncol = (int64_t)a->Kin * a->M;
-    if (!a->d_colptr) CUDA_TRY(cudaMalloc((void **)&a->d_colptr, sizeof(int64_t) * (size_t)(ncol + 1)));
     int64_t nnz = 0;
-    int s = sgc_asm_colptr(a, a->d_colptr, index_base, &nnz, nullptr);
+    int s = sgc_asm_count(a, &nnz, nullptr);
     if (s) return s;
+    if (!a->d_colptr) CUDA_TRY(cudaMalloc((void **)&a->d_colptr, sizeof(int64_t) * (size_t)(ncol + 1)));
     const size_t es = a->cx ? 16 : 8;
     int64_t *d_row = nullptr;
     void *d_val = nullptr;
@@ -1057,7 +1104,7 @@ extern "C" int sgc_asm_fill_host(sgc_asm *a, int64_t *colptr, int index_base, in
         cudaFree(d_row);
         return fail(SGC_ERR_NOMEM, "out of device memory for nzval");
     }
-    s = sgc_asm_fill(a, a->d_colptr, index_base, d_row, d_val, nullptr);
+    s = sgc_asm_fill_all(a, a->d_colptr, index_base, d_row, d_val, nullptr);
     if (!s) {
         cudaError_t e1 = cudaMemcpy(colptr, a->d_colptr, sizeof(int64_t) * (size_t)(ncol + 1), cudaMemcpyDeviceToHost);
         cudaError_t e2 = nnz ? cudaMemcpy(rowval, d_row, sizeof(int64_t) * (size_t)nnz, cudaMemcpyDeviceToHost) : cudaSuccess;

@@ -72,20 +72,25 @@ def _finish(a: _Asm, index_base, row_range, method, device, stream=None) -> Devi
     colptr = torch.empty(n.value + 1, dtype=torch.int64, device=dev)
     nnz = C.c_int64()
     st = stream_handle(stream)
-    check(lib.sgc_asm_colptr(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.byref(nnz), st))
+    # count pass (per-CTA totals + scan): returns nnz so that rowval / nzval can be allocated
+    check(lib.sgc_asm_count(a.h, C.byref(nnz), st))
     rowval = torch.empty(nnz.value, dtype=torch.int64, device=dev)
     nzval = torch.empty(nnz.value, dtype=vdt, device=dev)
-    if method == "direct":
+    if method == "direct":  # one pass: colptr + rowval + nzval
+        check(lib.sgc_asm_fill_all(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.c_void_p(rowval.data_ptr()),
+                                   C.c_void_p(nzval.data_ptr()), st))
+    elif method == "twostep":  # colptr first, then rowval / nzval from the given colptr
+        nnz2 = C.c_int64()
+        check(lib.sgc_asm_colptr(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.byref(nnz2), st))
+        assert nnz2.value == nnz.value
         check(lib.sgc_asm_fill(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.c_void_p(rowval.data_ptr()),
                                C.c_void_p(nzval.data_ptr()), st))
-    elif method == "coo":
-        colptr2 = torch.empty_like(colptr)
+    elif method == "coo":  # generic cross-check: COO triplets → stable radix sort → sum → drop zeros
         nnz2 = C.c_int64()
-        check(lib.sgc_asm_coo_sort(a.h, C.c_void_p(colptr2.data_ptr()), index_base, C.c_void_p(rowval.data_ptr()),
+        check(lib.sgc_asm_coo_sort(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.c_void_p(rowval.data_ptr()),
                                    C.c_void_p(nzval.data_ptr()), nnz.value, C.byref(nnz2), st))
         if nnz2.value != nnz.value:
             raise _lib.SgcError(_lib.SGC_ERR_INVALID, f"COO path found nnz = {nnz2.value}, closed form {nnz.value}")
-        colptr = colptr2
     else:
         raise ValueError(method)
     return DeviceCSC(m.value, n.value, colptr, rowval, nzval, index_base)

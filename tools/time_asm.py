@@ -16,27 +16,27 @@ def run(n, cplx, isbloch, cmpfirst=1):
     nnz = C.c_int64()
     st = stream_handle()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    check(lib.sgc_asm_colptr(h, C.c_void_p(colptr.data_ptr()), 1, C.byref(nnz), st))  # warm
+    check(lib.sgc_asm_count(h, C.byref(nnz), st))  # warm
     rowval = torch.empty(nnz.value, dtype=torch.int64, device="cuda")
     nzval = torch.empty(nnz.value, dtype=torch.complex128 if cplx else torch.float64, device="cuda")
-    check(lib.sgc_asm_fill(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()), C.c_void_p(nzval.data_ptr()), st))
+    check(lib.sgc_asm_fill_all(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()), C.c_void_p(nzval.data_ptr()), st))
     torch.cuda.synchronize()
     reps = 5
     ev[0].record()
     for _ in range(reps):
-        check(lib.sgc_asm_colptr(h, C.c_void_p(colptr.data_ptr()), 1, C.byref(nnz), st))
+        check(lib.sgc_asm_set_row_range(h, 0, 3 * M))  # invalidates the cached count
+        check(lib.sgc_asm_count(h, C.byref(nnz), st))
     ev[1].record()
     for _ in range(reps):
-        check(lib.sgc_asm_fill(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()), C.c_void_p(nzval.data_ptr()), st))
+        check(lib.sgc_asm_fill_all(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()), C.c_void_p(nzval.data_ptr()), st))
     ev[2].record()
     torch.cuda.synchronize()
     t_col, t_fill = ev[0].elapsed_time(ev[1]) / reps, ev[1].elapsed_time(ev[2]) / reps
     es = 16 if cplx else 8
     alg = nnz.value * (8 + es) + (3 * M + 1) * 8
-    print(json.dumps(dict(n=n, cplx=cplx, bloch=isbloch, nnz=nnz.value, colptr_ms=round(t_col, 3), fill_ms=round(t_fill, 3),
+    print(json.dumps(dict(n=n, cplx=cplx, bloch=isbloch, cmpfirst=cmpfirst, nnz=nnz.value, count_ms=round(t_col, 3), fill_all_ms=round(t_fill, 3),
                           total_ms=round(t_col + t_fill, 3), gnnz_s=round(nnz.value / (t_col + t_fill) / 1e6, 1),
-                          alg_gbs=round(alg / (t_col + t_fill) / 1e6), fill_gbs=round((nnz.value * (8 + es) + 3 * M * 8) / t_fill / 1e6),
-                          colptr_gbs=round(3 * M * 8 / t_col / 1e6))), flush=True)
+                          alg_gbs=round(alg / (t_col + t_fill) / 1e6), fill_gbs=round(alg / t_fill / 1e6))), flush=True)
     lib.sgc_asm_destroy(h)
 
 if __name__ == "__main__":
