@@ -90,10 +90,10 @@ SGC_D void block_entries(const AsmParams<T> &p, const AsmBlock<T> &B, IDX c, con
     }
 }
 
-template <typename T>
-SGC_D void cmpswap(int64_t &ra, T &va, int64_t &rb, T &vb) {
+template <typename R, typename T>
+SGC_D void cmpswap(R &ra, T &va, R &rb, T &vb) {
     if (rb < ra) {
-        const int64_t tr = ra; ra = rb; rb = tr;
+        const R tr = ra; ra = rb; rb = tr;
         const T tv = va; va = vb; vb = tv;
     }
 }
@@ -148,31 +148,46 @@ SGC_D int column_count_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3]
     return cnt;
 }
 
-// sorted entries of column (nu, c) in registers; returns the count
-template <typename T, typename IDX>
-SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3], int64_t (&rows)[ASM_MAX_ENTRIES],
-                            T (&vals)[ASM_MAX_ENTRIES]) {
-    constexpr int64_t INVALID = 0x7fffffffffffffffLL;
+// Sorting networks over (row, value) pairs held in registers; invalid slots carry the largest
+// row and sink to the end.  E = 2, 4 or 6 inputs.
+template <int E, typename R, typename T>
+SGC_D void sort_entries(R (&rows)[E], T (&vals)[E]) {
+    if (E == 2) {
+        cmpswap(rows[0], vals[0], rows[1], vals[1]);
+    } else if (E == 4) {
+        cmpswap(rows[0], vals[0], rows[1], vals[1]); cmpswap(rows[2], vals[2], rows[3], vals[3]);
+        cmpswap(rows[0], vals[0], rows[2], vals[2]); cmpswap(rows[1], vals[1], rows[3], vals[3]);
+        cmpswap(rows[1], vals[1], rows[2], vals[2]);
+    } else {
+        cmpswap(rows[0], vals[0], rows[5], vals[5]); cmpswap(rows[1], vals[1], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[4], vals[4]);
+        cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
+        cmpswap(rows[0], vals[0], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[5], vals[5]);
+        cmpswap(rows[0], vals[0], rows[1], vals[1]); cmpswap(rows[2], vals[2], rows[3], vals[3]); cmpswap(rows[4], vals[4], rows[5], vals[5]);
+        cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
+    }
+}
+
+// sorted entries of column (nu, c) in registers; returns the count.  R is the row type: 32-bit
+// when the matrix has fewer than 2^31 rows (half the register and ALU cost), else 64-bit.
+template <typename T, typename IDX, typename R, int E>
+SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3], R (&rows)[E], T (&vals)[E]) {
+    const R INVALID = (R)(sizeof(R) == 4 ? 0x7fffffff : 0x7fffffffffffffffLL);
 #pragma unroll
-    for (int q = 0; q < ASM_MAX_ENTRIES; ++q) { rows[q] = INVALID; vals[q] = zero_of(T{}); }
+    for (int q = 0; q < E; ++q) { rows[q] = INVALID; vals[q] = zero_of(T{}); }
     int cnt = 0;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
+    for (int q = 0; q < E / 2; ++q) {
         if (q < p.nblk_of[nu]) {
             T v[2];
             int64_t r[2];
             bool ok[2];
             block_entries<T, IDX>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
             cnt += (int)ok[0] + (int)ok[1];
-            if (ok[0]) { rows[2 * q] = r[0]; vals[2 * q] = v[0]; }
-            if (ok[1]) { rows[2 * q + 1] = r[1]; vals[2 * q + 1] = v[1]; }
+            if (ok[0]) { rows[2 * q] = (R)r[0]; vals[2 * q] = v[0]; }
+            if (ok[1]) { rows[2 * q + 1] = (R)r[1]; vals[2 * q + 1] = v[1]; }
         }
     }
-    cmpswap(rows[0], vals[0], rows[5], vals[5]); cmpswap(rows[1], vals[1], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[4], vals[4]);
-    cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
-    cmpswap(rows[0], vals[0], rows[3], vals[3]); cmpswap(rows[2], vals[2], rows[5], vals[5]);
-    cmpswap(rows[0], vals[0], rows[1], vals[1]); cmpswap(rows[2], vals[2], rows[3], vals[3]); cmpswap(rows[4], vals[4], rows[5], vals[5]);
-    cmpswap(rows[1], vals[1], rows[2], vals[2]); cmpswap(rows[3], vals[3], rows[4], vals[4]);
+    sort_entries<E>(rows, vals);
     return cnt;
 }
 
@@ -202,30 +217,38 @@ SGC_D int block_exclusive_scan(int v, int *s_warp, int &total) {
     return incl - v + (wid ? s_warp[32 + wid - 1] : 0);
 }
 
-template <typename T, typename IDX, int BLOCK, int MODE>
+// NCOLS = columns per group (1..3), E = entry slots per column (2, 4 or 6).  In the FILL modes
+// the group's entries are computed ONCE into registers (NCOLS·E ≤ 12 slots), then the block scan
+// of the per-thread totals gives their position.
+template <typename T, typename IDX, typename R, int BLOCK, int MODE, int NCOLS, int E>
 __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ AsmParams<T> p,
                                                      int64_t *__restrict__ cta_total,        // COUNT: out
                                                      const int64_t *__restrict__ cta_offset,  // COLPTR / FILL_ALL: in
                                                      const int64_t *__restrict__ colptr_in,   // FILL: in
                                                      int64_t *__restrict__ colptr_out,        // COLPTR / FILL_ALL: out
-                                                     int64_t *__restrict__ rowval, T *__restrict__ nzval, int max_per_group) {
+                                                     int64_t *__restrict__ rowval, T *__restrict__ nzval) {
     __shared__ int s_warp[64];
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool WRITES = (MODE == ASM_FILL || MODE == ASM_FILL_ALL);
     const int64_t g0 = (int64_t)blockIdx.x * BLOCK;
     const int64_t g = g0 + threadIdx.x;
     const bool live = g < p.ngroups;
     int nu0 = 0;
     IDX c = 0, sub[3] = {0, 0, 0};
     if (live) group_decode<T, IDX>(p, g, nu0, c, sub);
-    const int ncols = p.cols_per_group;
 
-    // per-column counts of my group
-    int cnt[3] = {0, 0, 0};
+    int cnt[NCOLS];
+    R rows[WRITES ? NCOLS : 1][E];
+    T vals[WRITES ? NCOLS : 1][E];
     int mine = 0;
-    if (live) {
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < ncols) { cnt[q] = column_count_of<T, IDX>(p, nu0 + q, c, sub); mine += cnt[q]; }
+    for (int q = 0; q < NCOLS; ++q) {
+        cnt[q] = 0;
+        if (live) {
+            if (WRITES) cnt[q] = column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows[WRITES ? q : 0], vals[WRITES ? q : 0]);
+            else cnt[q] = column_count_of<T, IDX>(p, nu0 + q, c, sub);
+        }
+        mine += cnt[q];
     }
     int total;
     const int off0 = block_exclusive_scan<BLOCK>(mine, s_warp, total);
@@ -234,40 +257,66 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
         return;
     }
     // absolute (0-based) position of this CTA's first entry
-    const int64_t col0 = g0 * ncols;
+    const int64_t col0 = g0 * NCOLS;
     const int64_t base = (MODE == ASM_FILL) ? colptr_in[col0] - p.index_base : cta_offset[blockIdx.x];
     if (MODE == ASM_COLPTR || MODE == ASM_FILL_ALL) {
         if (live) {
             int64_t o = base + off0 + p.index_base;
-            const int64_t col = g * ncols;
+            const int64_t col = g * NCOLS;
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-                if (q < ncols) { colptr_out[col + q] = o; o += cnt[q]; }
+            for (int q = 0; q < NCOLS; ++q) { colptr_out[col + q] = o; o += cnt[q]; }
             if (g == p.ngroups - 1) colptr_out[p.ncol] = o;  // one-past-the-end entry
         }
         if (MODE == ASM_COLPTR) return;
     }
-    T *s_vals = reinterpret_cast<T *>(smem_raw);
-    int64_t *s_rows = reinterpret_cast<int64_t *>(smem_raw + sizeof(T) * (size_t)BLOCK * max_per_group);
-    if (live) {
-        int o = off0;
+    if (WRITES) {
+        T *s_vals = reinterpret_cast<T *>(smem_raw);
+        R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)BLOCK * NCOLS * E);
+        if (live) {
+            int o = off0;
 #pragma unroll
-        for (int q = 0; q < 3; ++q)
-            if (q < ncols) {
-                int64_t rows[ASM_MAX_ENTRIES];
-                T vals[ASM_MAX_ENTRIES];
-                column_entries_of<T, IDX>(p, nu0 + q, c, sub, rows, vals);
+            for (int q = 0; q < NCOLS; ++q) {
 #pragma unroll
-                for (int e = 0; e < ASM_MAX_ENTRIES; ++e)
-                    if (e < cnt[q]) { s_rows[o + e] = rows[e] + p.index_base; s_vals[o + e] = vals[e]; }
+                for (int e = 0; e < E; ++e)
+                    if (e < cnt[q]) { s_rows[o + e] = rows[WRITES ? q : 0][e]; s_vals[o + e] = vals[WRITES ? q : 0][e]; }
                 o += cnt[q];
             }
+        }
+        __syncthreads();
+        const int64_t ib = p.index_base;
+        for (int q = threadIdx.x; q < total; q += BLOCK) {
+            rowval[base + q] = (int64_t)s_rows[q] + ib;
+            stg_stream(nzval + base + q, s_vals[q]);
+        }
     }
-    __syncthreads();
-    for (int q = threadIdx.x; q < total; q += BLOCK) {
-        rowval[base + q] = s_rows[q];
-        stg_stream(nzval + base + q, s_vals[q]);
+}
+
+// Count pass when all rows are kept (no row partition): the number of stored entries of a column
+// is separable, count(nu, c) = A[nu][0][i] + A[nu][1][j] + A[nu][2][k], where A[nu][a][·] counts
+// the nonzero diagonal / off-diagonal values of the blocks of block column nu that act along
+// axis a (host-built from the same V₀/Vₛ tables, O(ΣN)).  The kernel only sums three small table
+// entries per column and reduces them per CTA.
+struct AsmCountTables {
+    const int *A[3][3];  // [nu][axis] → int[N_axis]
+};
+
+template <typename IDX, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_asm_count_fast(AsmCountTables t, int cols_per_group, int Kin, int64_t M,
+                                                          int64_t ngroups, IDX n0, IDX n1, int64_t *__restrict__ cta_total) {
+    __shared__ int s_warp[64];
+    const int64_t g = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    int mine = 0;
+    if (g < ngroups) {
+        int nu0 = 0;
+        IDX c;
+        if (cols_per_group > 1 || Kin == 1) c = (IDX)g;
+        else { nu0 = (g >= 2 * M) ? 2 : (g >= M ? 1 : 0); c = (IDX)(g - (int64_t)nu0 * M); }
+        const IDX q = c / n0, i = c - q * n0, k = q / n1, j = q - k * n1;
+        for (int nu = nu0; nu < nu0 + cols_per_group; ++nu) mine += t.A[nu][0][i] + t.A[nu][1][j] + t.A[nu][2][k];
     }
+    int total;
+    block_exclusive_scan<BLOCK>(mine, s_warp, total);
+    if (threadIdx.x == 0) cta_total[blockIdx.x] = total;
 }
 
 // y += A x   (CSC, one thread per column) — test utility mirroring `mul!(g, Curl, f)`.

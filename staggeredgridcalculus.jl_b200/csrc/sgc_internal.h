@@ -86,6 +86,8 @@ struct sgc_asm {
     int64_t *cta_total = nullptr, *cta_offset = nullptr;  // per-CTA entry counts and their exclusive scan
     int64_t ncta = 0;
     bool counted = false;
+    int *count_tables = nullptr;              // device: A[nu][axis][N_axis] of the separable count
+    size_t count_off[3][3] = {};              // element offsets into count_tables
     // host convenience
     int64_t *d_colptr = nullptr;
 };

@@ -32,7 +32,8 @@ int sgc_fail(int code, const char *fmt, ...) {
 
 int sgc_check_launch(const char *what) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) cudaGetLastError();
     if (e != cudaSuccess) return sgc_fail(SGC_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
     return SGC_OK;
 }
@@ -711,13 +712,23 @@ extern "C" int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int
 // =============================================================================================
 // sparse assembly
 // =============================================================================================
+static void free_checked(void *p, const char *what) {
+    if (!p) return;
+    cudaError_t e = cudaFree(p);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "libsgc_b200: cudaFree(%s) failed: %s\n", what, cudaGetErrorString(e));
+        cudaGetLastError();  // do not let a failed free poison the next launch check
+    }
+}
+
 extern "C" int sgc_asm_destroy(sgc_asm *a) {
     if (!a) return SGC_OK;
-    if (a->arena) cudaFree(a->arena);
-    if (a->scan_tmp) cudaFree(a->scan_tmp);
-    if (a->d_colptr) cudaFree(a->d_colptr);
-    if (a->cta_total) cudaFree(a->cta_total);
-    if (a->cta_offset) cudaFree(a->cta_offset);
+    free_checked(a->arena, "asm arena");
+    free_checked(a->scan_tmp, "scan scratch");
+    free_checked(a->d_colptr, "host-path colptr");
+    free_checked(a->cta_total, "cta totals");
+    free_checked(a->cta_offset, "cta offsets");
+    free_checked(a->count_tables, "count tables");
     delete a;
     return SGC_OK;
 }
@@ -804,6 +815,33 @@ static int finish_asm(sgc_asm *a) {
     if (b.host.size()) CUDA_TRY(cudaMemcpy(a->arena, b.host.data(), b.host.size(), cudaMemcpyHostToDevice));
     a->row_begin = 0;
     a->row_end = (int64_t)a->Kout * a->M;
+    // separable count tables: A[nu][axis][i] = number of nonzero values the blocks of block column
+    // nu acting along `axis` store in a column whose subscript along that axis is i
+    std::vector<int> tab;
+    for (int nu = 0; nu < 3; ++nu)
+        for (int ax = 0; ax < 3; ++ax) {
+            a->count_off[nu][ax] = tab.size();
+            tab.resize(tab.size() + (size_t)a->N[ax], 0);
+        }
+    auto nonzero = [](const HV &v) { return v.re != 0.0 || (v.cx && v.im != 0.0); };
+    for (auto &B : a->blocks) {
+        int *A = tab.data() + a->count_off[B.nu][B.axis];
+        const int64_t Nw = a->N[B.axis];
+        if (B.ns == 0) {  // diagonal-only block: the same count for every cell
+            for (int64_t i = 0; i < Nw; ++i) A[i] += nonzero(B.V0[0]) ? 1 : 0;
+        } else if (Nw == 1) {
+            A[0] += nonzero(hadd(B.V0[0], B.Vs[0])) ? 1 : 0;
+        } else {
+            for (int64_t i = 0; i < Nw; ++i) {
+                int64_t rw = i - B.ns;
+                if (rw < 0) rw += Nw;
+                if (rw >= Nw) rw -= Nw;
+                A[i] += (nonzero(B.V0[i]) ? 1 : 0) + (nonzero(B.Vs[rw]) ? 1 : 0);
+            }
+        }
+    }
+    CUDA_TRY(cudaMalloc((void **)&a->count_tables, sizeof(int) * tab.size()));
+    CUDA_TRY(cudaMemcpy(a->count_tables, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
     return SGC_OK;
 }
 
@@ -974,39 +1012,49 @@ static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
 
 constexpr int ASM_BLOCK = 128;
 
-static int asm_max_per_group(const sgc_asm *a) {
-    int per_nu[3] = {0, 0, 0}, nb[3] = {0, 0, 0};
-    for (auto &B : a->blocks) { per_nu[B.nu] += (B.ns == 0 ? 1 : 2); nb[B.nu]++; }
-    for (int nu = 0; nu < 3; ++nu)
-        if (nb[nu] > 3 || per_nu[nu] > ASM_MAX_ENTRIES) return -1;
-    if (a->cmpfirst) return std::max(1, per_nu[0] + per_nu[1] + per_nu[2]);
-    return std::max(1, std::max(per_nu[0], std::max(per_nu[1], per_nu[2])));
+// entry slots per column needed by this operator: 2, 4 or 6 (2 per block in the block column)
+static int asm_slots_per_col(const sgc_asm *a) {
+    int nb[3] = {0, 0, 0};
+    for (auto &B : a->blocks) nb[B.nu]++;
+    const int m = std::max(nb[0], std::max(nb[1], nb[2]));
+    if (m > 3) return -1;
+    return 2 * std::max(1, m);
 }
 
-template <typename T, typename IDX, int MODE>
+template <typename T, typename IDX, typename R, int MODE, int NCOLS, int E>
 static int asm_launch(const sgc_asm *a, int index_base, const int64_t *colptr_in, int64_t *colptr_out, int64_t *rowval,
                       T *nzval, cudaStream_t st) {
     AsmParams<T> p = asm_params<T>(a, index_base);
-    const int maxg = asm_max_per_group(a);
-    if (maxg < 0) return fail(SGC_ERR_INVALID, "operator has more than %d entries per column", ASM_MAX_ENTRIES);
     if (a->ncta == 0) return SGC_OK;
     const bool needs_smem = (MODE == ASM_FILL || MODE == ASM_FILL_ALL);
-    const size_t smem = needs_smem ? (sizeof(T) + sizeof(int64_t)) * (size_t)ASM_BLOCK * maxg : 0;
-    auto kern = k_asm_group<T, IDX, ASM_BLOCK, MODE>;
+    const size_t smem = needs_smem ? (sizeof(T) + sizeof(R)) * (size_t)ASM_BLOCK * NCOLS * E : 0;
+    auto kern = k_asm_group<T, IDX, R, ASM_BLOCK, MODE, NCOLS, E>;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)a->ncta, ASM_BLOCK, smem, st>>>(p, a->cta_total, a->cta_offset, colptr_in, colptr_out, rowval, nzval, maxg);
+    kern<<<(unsigned)a->ncta, ASM_BLOCK, smem, st>>>(p, a->cta_total, a->cta_offset, colptr_in, colptr_out, rowval, nzval);
     return check_launch("k_asm_group");
+}
+
+template <typename T, typename IDX, typename R, int MODE>
+static int asm_shape_dispatch(const sgc_asm *a, int index_base, const int64_t *ci, int64_t *co, int64_t *rv, T *nz, cudaStream_t st) {
+    const int ncols = a->cmpfirst ? a->Kin : 1;
+    const int e = asm_slots_per_col(a);
+    if (e < 0 || ncols * e > 12)
+        return fail(SGC_ERR_INVALID, "operator needs %d columns x %d entry slots per group (limit 12)", ncols, e);
+#define ASM_CASE(NC, EE) if (ncols == NC && e == EE) return asm_launch<T, IDX, R, MODE, NC, EE>(a, index_base, ci, co, rv, nz, st);
+    ASM_CASE(1, 2) ASM_CASE(1, 4) ASM_CASE(1, 6) ASM_CASE(2, 2) ASM_CASE(2, 4) ASM_CASE(2, 6) ASM_CASE(3, 2) ASM_CASE(3, 4)
+#undef ASM_CASE
+    return fail(SGC_ERR_INVALID, "unsupported assembly shape");
 }
 
 template <int MODE>
 static int asm_dispatch(const sgc_asm *a, int index_base, const int64_t *colptr_in, int64_t *colptr_out, int64_t *rowval,
                         void *nzval, cudaStream_t st) {
-    const int64_t ncol = (int64_t)a->Kin * a->M;
-    const bool small = ncol < (int64_t)0xffffffffLL && a->M < (int64_t)0xffffffffLL;
-    if (a->cx) return small ? asm_launch<cplx, uint32_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (cplx *)nzval, st)
-                            : asm_launch<cplx, uint64_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (cplx *)nzval, st);
-    return small ? asm_launch<double, uint32_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (double *)nzval, st)
-                 : asm_launch<double, uint64_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (double *)nzval, st);
+    const int64_t ncol = (int64_t)a->Kin * a->M, nrow = (int64_t)a->Kout * a->M;
+    const bool small = ncol < (int64_t)0x7fffffffLL && nrow < (int64_t)0x7fffffffLL;  // 32-bit cell / row arithmetic
+    if (a->cx) return small ? asm_shape_dispatch<cplx, uint32_t, int32_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (cplx *)nzval, st)
+                            : asm_shape_dispatch<cplx, uint64_t, int64_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (cplx *)nzval, st);
+    return small ? asm_shape_dispatch<double, uint32_t, int32_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (double *)nzval, st)
+                 : asm_shape_dispatch<double, uint64_t, int64_t, MODE>(a, index_base, colptr_in, colptr_out, rowval, (double *)nzval, st);
 }
 
 // pass 1: per-CTA totals + their exclusive scan; leaves nnz in the handle (synchronises)
@@ -1024,7 +1072,21 @@ static int asm_count(sgc_asm *a, cudaStream_t st) {
         CUDA_TRY(cudaMalloc((void **)&a->cta_offset, sizeof(int64_t) * (size_t)(ncta + 1)));
         a->ncta = ncta;
     }
-    int s = asm_dispatch<ASM_COUNT>(a, 0, nullptr, nullptr, nullptr, nullptr, st);
+    int s;
+    if (a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M) {  // all rows kept: separable count
+        AsmCountTables t;
+        for (int nu = 0; nu < 3; ++nu)
+            for (int ax = 0; ax < 3; ++ax) t.A[nu][ax] = a->count_tables + a->count_off[nu][ax];
+        const int cpg = a->cmpfirst ? a->Kin : 1;
+        const bool small = (int64_t)a->Kin * a->M < (int64_t)0x7fffffffLL;
+        if (small)
+            k_asm_count_fast<uint32_t, ASM_BLOCK><<<(unsigned)ncta, ASM_BLOCK, 0, st>>>(t, cpg, a->Kin, a->M, ngroups, (uint32_t)a->N[0], (uint32_t)a->N[1], a->cta_total);
+        else
+            k_asm_count_fast<uint64_t, ASM_BLOCK><<<(unsigned)ncta, ASM_BLOCK, 0, st>>>(t, cpg, a->Kin, a->M, ngroups, (uint64_t)a->N[0], (uint64_t)a->N[1], a->cta_total);
+        s = check_launch("k_asm_count_fast");
+    } else {
+        s = asm_dispatch<ASM_COUNT>(a, 0, nullptr, nullptr, nullptr, nullptr, st);
+    }
     if (s) return s;
     CUDA_TRY(cudaMemsetAsync(a->cta_total + ncta, 0, sizeof(int64_t), st));
     size_t need = 0;
