@@ -113,7 +113,7 @@ def cpu_reference_rate(dlinv_prim, dlinv_dual, nz, target_seconds, threads=None)
         step()
         n += 1
         dt = time.perf_counter() - t0
-        if dt >= target_seconds or n >= 50:
+        if dt >= target_seconds or n >= 2000:
             break
     rate = 2 * M * n / dt / 1e9
     return rate, threads, f"{n} curl-of-curl passes on 256x256x{nz} ComplexF64 (same inputs family), {dt:.1f} s wall"
@@ -122,7 +122,7 @@ def cpu_reference_rate(dlinv_prim, dlinv_dual, nz, target_seconds, threads=None)
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    nz = 64  # bounded sample: a 256×256×64 z-slab of the workload (per-cell cost is size independent)
+    nz = NLOCAL[2]  # one rank's full 256^3 grid of the workload; a step is one curl-of-curl pass over it
     dprim, ddual = build_inputs(NLOCAL[2] * max(1, args.gpus))
     # the driver's K/W apply to "steps" of the bounded sample
     from oracle import c_oracle as CO
@@ -148,7 +148,7 @@ def run_reference(args, rank, world):
         step()
     dt = time.perf_counter() - t0
     val = 2 * M * args.steps / dt / 1e9
-    sample = f"{args.steps} curl-of-curl passes on a 256x256x{nz} slab of the workload, {dt:.2f} s wall"
+    sample = f"{args.steps} curl-of-curl passes on the 256x256x{nz} grid of one rank, {dt:.2f} s wall"
     out = {
         "impl": "reference", "metric": "curl_apply_gcell_per_s", "value": val, "unit": "Gcell/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
@@ -299,7 +299,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": workload_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_curl3<cplx,cplx,false,TX,TY>",
+                     "traffic": None, "kernel": "k_curl3p<cplx,cplx,ADD=0,32x4 tile,4-stage cp.async ring>",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * M},
@@ -318,7 +318,7 @@ def main():
     if world == 1 and not args.no_assembly:
         out["assembly"] = bench_assembly(S, torch, peak)
     if world == 1 and not args.no_cpu_baseline:
-        rate, threads, sample = cpu_reference_rate(dprim, ddual, 64, args.cpu_seconds)
+        rate, threads, sample = cpu_reference_rate(dprim, ddual, NLOCAL[2], args.cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
     print(json.dumps(out), flush=True)
     if world > 1:
@@ -328,30 +328,50 @@ def main():
 
 def bench_assembly(S, torch, peak):
     """Second half of the metric: create_curl CSC assembly in nnz/s (BASELINE.json configs[3]:
-    512³, Float64, uniform, all-Bloch, nnz = 12·512³ = 1 610 612 736)."""
+    512³, Float64, uniform, all-Bloch, nnz = 12·512³ = 1 610 612 736), through the C ABI with
+    caller-owned output arrays (what the Julia shim does): count pass + scan + nnz read-back, then
+    the single fill pass that writes colptr, rowval and nzval."""
+    import ctypes as C
+    from sgc_b200._lib import lib, check
+    from sgc_b200.device import ints, int64s, scalars2, stream_handle
     n = 512
     N = (n, n, n)
+    M = n ** 3
     res = {}
     try:
+        h = C.c_void_p()
+        check(lib.sgc_asm_create_curl(C.byref(h), 3, int64s(N), ints([1, 1, 1]), None, 0, ints([1, 1, 1]),
+                                      scalars2([1.0] * 3), 0, ints([1, 2, 3]), 3, ints([1, 2, 3]), 3, ints([1, 2, 3]), 1))
+        st = stream_handle()
+        nnz = C.c_int64()
+        check(lib.sgc_asm_count(h, C.byref(nnz), st))
+        colptr = torch.empty(3 * M + 1, dtype=torch.int64, device="cuda")
+        rowval = torch.empty(nnz.value, dtype=torch.int64, device="cuda")
+        nzval = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+
+        def once():
+            check(lib.sgc_asm_set_row_range(h, 0, 3 * M))  # drops the cached count: time the whole assembly
+            check(lib.sgc_asm_count(h, C.byref(nnz), st))
+            check(lib.sgc_asm_fill_all(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()),
+                                       C.c_void_p(nzval.data_ptr()), st))
+        for _ in range(2):
+            once()
         torch.cuda.synchronize()
-        A = S.create_curl([True] * 3, None, N=N)  # warm-up (allocations, scan scratch)
-        nnz = A.nnz
-        del A
-        torch.cuda.empty_cache()
-        reps = 3
+        reps = 5
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         for _ in range(reps):
-            A = S.create_curl([True] * 3, None, N=N)
-            del A
+            once()
         ev1.record()
         torch.cuda.synchronize()
         ms = ev0.elapsed_time(ev1) / reps
-        alg = nnz * 16 + (3 * n ** 3 + 1) * 8
-        res = {"workload": "create_curl 512^3 Float64 uniform all-Bloch, order_cmpfirst=true, colptr+rowval+nzval on device",
-               "nnz": nnz, "ms": ms, "nnz_per_s": nnz / (ms * 1e-3), "algorithmic_bytes": alg,
-               "achieved_gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak,
-               "includes": "table upload, count+scan (colptr), nnz read-back, output allocation, fill"}
+        ok = bool((colptr[1:] - colptr[:-1] == 4).all()) and int(colptr[-1]) == nnz.value + 1
+        lib.sgc_asm_destroy(h)
+        alg = nnz.value * 16 + (3 * M + 1) * 8
+        res = {"workload": "create_curl 512^3 Float64 uniform all-Bloch, order_cmpfirst=true; colptr+rowval+nzval on device (29.0 GB)",
+               "nnz": nnz.value, "ms": ms, "nnz_per_s": nnz.value / (ms * 1e-3), "algorithmic_bytes": alg,
+               "achieved_gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak, "structure_ok": ok,
+               "includes": "count pass + scan + nnz read-back (host sync) + single fill pass"}
     except Exception as ex:  # out of memory on a shared box etc.
         res = {"error": str(ex)[:200]}
     return res
