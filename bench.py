@@ -177,6 +177,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--graph", default="off", choices=["on", "off"])
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -207,17 +209,32 @@ def main():
     dprim, ddual = build_inputs(nz_total)
     k0, k1 = rank * NLOCAL[2], (rank + 1) * NLOCAL[2]
     bl, e = [False] * 3, [1.0] * 3
-    # E -> H: forward differences with ∆l⁻¹ at dual points; H -> E': backward, primal points
-    c_dual = SlabCurl(S.SGC_C128, NLOCAL, [True] * 3, [ddual[0], ddual[1], ddual[2][k0:k1]], bl, e, rank, world)
-    c_prim = SlabCurl(S.SGC_C128, NLOCAL, [False] * 3, [dprim[0], dprim[1], dprim[2][k0:k1]], bl, e, rank, world)
+    # E -> H: forward differences with ∆l⁻¹ at dual points; H -> E': backward, primal points.
+    # N > 1: fields live in symmetric (peer-mapped) memory and the fused kernel reads its one-plane
+    # halo straight from the neighbour over NVLink; NCCL send/recv is the fallback transport.
+    arena, halo = None, "none"
+    if world > 1 and args.halo == "peer":
+        try:
+            from sgc_b200.slab import PeerArena
+            arena, halo = PeerArena(3 * 3 * M * 16 + 4096), "peer-memory loads inside the stencil kernel (symmetric memory, NVLink)"
+        except Exception as ex:
+            sys.stderr.write(f"[bench] symmetric memory unavailable ({type(ex).__name__}: {str(ex)[:120]}); using NCCL halos\n")
+    if world > 1 and arena is None:
+        halo = "NCCL send/recv on a side stream, overlapped with the interior planes"
+    c_dual = SlabCurl(S.SGC_C128, NLOCAL, [True] * 3, [ddual[0], ddual[1], ddual[2][k0:k1]], bl, e, rank, world, arena=arena)
+    c_prim = SlabCurl(S.SGC_C128, NLOCAL, [False] * 3, [dprim[0], dprim[1], dprim[2][k0:k1]], bl, e, rank, world, arena=arena)
 
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     def rnd():
         return torch.complex(torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1,
                              torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
-    E = S.DeviceArray(rnd(), NLOCAL + (3,))
-    H = S.DeviceArray.zeros(NLOCAL + (3,))
-    E2 = S.DeviceArray.zeros(NLOCAL + (3,))
+    if arena is not None:
+        E, H, E2 = (arena.array(NLOCAL + (3,)) for _ in range(3))
+        E.t.copy_(rnd()); H.t.zero_(); E2.t.zero_()
+    else:
+        E = S.DeviceArray(rnd(), NLOCAL + (3,))
+        H = S.DeviceArray.zeros(NLOCAL + (3,))
+        E2 = S.DeviceArray.zeros(NLOCAL + (3,))
 
     def step():
         c_dual.apply(H, E, "=")
@@ -231,18 +248,47 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    # The step is launch-bound on the host for N > 1 (kernels + NCCL p2p + stream joins per curl), so
+    # it is captured once into a CUDA graph and replayed: streams and graphs instead of host work.
+    graph, launches_per_step, run_step = None, None, step
+    if args.graph == "on" and world == 1:  # torch's NCCL p2p ops hang under capture (measured): N = 1 only
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                g = torch.cuda.CUDAGraph()
+                l0 = S.launch_count()
+                with torch.cuda.graph(g, stream=side):
+                    step()
+                launches_per_step = S.launch_count() - l0
+            torch.cuda.current_stream().wait_stream(side)
+            g.replay()
+            torch.cuda.synchronize()
+            graph, run_step = g, g.replay
+        except Exception as ex:  # capture unsupported for some op: stay eager
+            sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:120]}); running eagerly\n")
+            graph, run_step = None, step
+            torch.cuda.synchronize()
+    ok_flags = torch.tensor([1 if graph is not None else 0], device="cuda")
+    if world > 1:  # all ranks must take the same path (a replay contains the NCCL ops)
+        dist.all_reduce(ok_flags, op=dist.ReduceOp.MIN)
+        if int(ok_flags.item()) == 0:
+            graph, run_step = None, step
+    barrier()
     launches0 = S.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    t_host0 = time.perf_counter()
     for _ in range(args.steps):
-        step()
+        run_step()
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # host time to enqueue one step
     ev1.record()
     barrier()
     ms_total = ev0.elapsed_time(ev1)
     clocks = sampler.result()
-    launches = S.launch_count() - launches0
+    launches = (launches_per_step * args.steps) if graph is not None else (S.launch_count() - launches0)
     if world > 1:
         t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -307,6 +353,9 @@ def main():
         "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
         "gpu_launches": int(launches),
+        "cuda_graph": graph is not None,
+        "halo_transport": halo,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
     }
     tr = os.path.join(ROOT, "profiles", "curl3_traffic.json")
     if os.path.exists(tr):
