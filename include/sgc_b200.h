@@ -125,7 +125,8 @@ int sgc_op_set_slab(sgc_op *op, int lo_interface, int hi_interface);
 
 /* Kernel tuning knobs of the fused curl (0 keeps the default): tile size, z-march length, and
  * `variant`: low 4 bits select the kernel (0 = cp.async shared-memory ring [default], 1 =
- * register-prefetch z-march, 2 = unfused per-block sweeps, the reference's own structure);
+ * register-prefetch z-march, 2 = unfused per-block sweeps, the reference's own structure;
+ * for single-block operators 3 = force the scalar k_term kernel instead of the vectorised ones);
  * bits 4-7 give the number of ring stages for kernel 0 (0 = default 4), bits 8-11 the
  * CTAs-per-SM register target it was compiled for (0 = default). */
 int sgc_op_set_tuning(sgc_op *op, int tile_x, int tile_y, int march_z, int variant);

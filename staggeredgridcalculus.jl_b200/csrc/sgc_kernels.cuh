@@ -128,6 +128,197 @@ __global__ void __launch_bounds__(256) k_term(const __grid_constant__ TermParams
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Vectorised single-term kernels (the fast path of k_term)
+// ---------------------------------------------------------------------------------------------
+// Same formulas, evaluated from values already in registers: `nb` is the value at i+1 (forward)
+// or i−1 (backward); at the physical / slab face it is the RAW ghost value.
+template <typename T, typename C, int KIND>
+SGC_D T term_eval(const TermParams<T, C> &p, int64_t i, T cur, T nb) {
+    const int64_t Nw = p.Nw;
+    if (p.fwd) {
+        if (i == Nw - 1) {
+            if (p.bc_hi == BC_SYM) {
+                if (KIND == KIND_PARTIAL) return neg(mul(p.c[i], cur));
+                if (KIND == KIND_MEAN_ARITH) return mul(p.a2, cur);
+                return mul(mul(p.c[i], p.w[i]), cur);
+            }
+            if (p.bc_hi == BC_BLOCH) {
+                if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(mul_e(p.e, nb, p.e_real), cur));
+                if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(mul_e(p.e, nb, p.e_real), cur));
+                return mul(p.c[i], add(mul(p.w_hi, nb), mul(p.w[i], cur)));
+            }
+            if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(nb, cur));
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(nb, cur));
+            return mul(p.c[i], add(mul(p.w_hi, nb), mul(p.w[i], cur)));
+        }
+        if (i == 0 && p.bc_lo == BC_SYM) {
+            if (KIND == KIND_PARTIAL) return mul(p.c[0], nb);
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a2, nb);
+            return mul(mul(p.c[0], p.w[1]), nb);
+        }
+        if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(nb, cur));
+        if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(nb, cur));
+        return mul(p.c[i], add(mul(p.w[i + 1], nb), mul(p.w[i], cur)));
+    }
+    if (i == 0) {
+        if (p.bc_lo == BC_SYM) {
+            if (KIND == KIND_PARTIAL) return zero_of(cur);
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a1, cur);
+            return mul(mul(p.b0, p.w[0]), cur);
+        }
+        if (p.bc_lo == BC_BLOCH) {
+            if (KIND == KIND_PARTIAL) return mul(p.c[0], sub(cur, div_e(nb, p.e, p.e_real)));
+            if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, div_e(nb, p.e, p.e_real)));
+            return mul(p.c[0], add(mul(p.w[0], cur), div_e(mul(p.w_lo, nb), p.e, p.e_real)));
+        }
+        if (KIND == KIND_PARTIAL) return mul(p.c[0], sub(cur, nb));
+        if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, nb));
+        return mul(p.c[0], add(mul(p.w[0], cur), mul(p.w_lo, nb)));
+    }
+    if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(cur, nb));
+    if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, nb));
+    return mul(p.c[i], add(mul(p.w[i], cur), mul(p.w[i - 1], nb)));
+}
+
+// VEC consecutive elements (VEC·sizeof(T) is a multiple of 16 bytes, address 16-byte aligned)
+template <typename T, int VEC>
+SGC_D void ldg_vec_stream(T (&v)[VEC], const T *ptr) {
+    constexpr int CH = VEC * (int)sizeof(T) / 16;
+    double2 t[CH];
+#pragma unroll
+    for (int q = 0; q < CH; ++q)
+        asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(t[q].x), "=d"(t[q].y) : "l"(reinterpret_cast<const double2 *>(ptr) + q));
+    const double *d = reinterpret_cast<const double *>(t);
+    double *o = reinterpret_cast<double *>(v);
+#pragma unroll
+    for (int q = 0; q < 2 * CH; ++q) o[q] = d[q];
+}
+template <typename T, int VEC>
+SGC_D void ldg_vec_plain(T (&v)[VEC], const T *ptr) {
+    constexpr int CH = VEC * (int)sizeof(T) / 16;
+    double *o = reinterpret_cast<double *>(v);
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+        const double2 t = reinterpret_cast<const double2 *>(ptr)[q];
+        o[2 * q] = t.x; o[2 * q + 1] = t.y;
+    }
+}
+template <typename T, int VEC>
+SGC_D void stg_vec_stream(T *ptr, const T (&v)[VEC]) {
+    constexpr int CH = VEC * (int)sizeof(T) / 16;
+    const double *d = reinterpret_cast<const double *>(v);
+#pragma unroll
+    for (int q = 0; q < CH; ++q)
+        asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1,%2};" ::"l"(reinterpret_cast<double2 *>(ptr) + q), "d"(d[2 * q]), "d"(d[2 * q + 1]) : "memory");
+}
+
+// Operator along the contiguous axis (inner == 1): each thread owns VEC consecutive elements of R
+// rows; the neighbour across the vector boundary comes from the adjacent lane by shuffle, the
+// warp-edge lane fetches it (or the wrap / ghost element) itself.
+template <typename T, typename C, int KIND, bool ADD, int VEC, int R>
+__global__ void __launch_bounds__(256) k_term_x(const __grid_constant__ TermParams<T, C> p) {
+    const int64_t Nw = p.Nw;
+    const int64_t iv = ((int64_t)blockIdx.x * 256 + threadIdx.x) * VEC;
+    const int lane = threadIdx.x & 31;
+    const bool active = iv < Nw;
+    const int fwd = p.fwd;
+    const bool edge = fwd ? (lane == 31 || iv + VEC >= Nw) : (lane == 0);
+    const int64_t nbi = fwd ? iv + VEC : iv - 1;  // index of the element beyond my vector
+    const bool nb_inside = (nbi >= 0 && nbi < Nw);
+    const bool nb_ghost = fwd ? (p.bc_hi != BC_SYM) : (p.bc_lo != BC_SYM);
+    const T Z = zero_of(T{});
+    for (int64_t o0 = p.o_begin + (int64_t)blockIdx.y * R; o0 < p.o_end; o0 += (int64_t)gridDim.y * R) {
+        T cur[R][VEC];
+        T nb[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool live = active && (o0 + r < p.o_end);
+            if (live) ldg_vec_stream<T, VEC>(cur[r], p.F + (o0 + r) * Nw + iv);
+            else {
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) cur[r][e] = Z;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const bool live = active && (o0 + r < p.o_end);
+            T got = fwd ? shfl_down1(cur[r][0]) : shfl_up1(cur[r][VEC - 1]);
+            if (edge && live) {
+                if (nb_inside) got = ldg_stream(p.F + (o0 + r) * Nw + nbi);
+                else got = nb_ghost ? ldg_plain(p.ghost + (o0 + r) * p.ghost_stride_o) : Z;
+            }
+            nb[r] = got;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (!(active && (o0 + r < p.o_end))) continue;
+            T out[VEC];
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) {
+                const T n = fwd ? (e < VEC - 1 ? cur[r][e + 1 < VEC ? e + 1 : e] : nb[r]) : (e > 0 ? cur[r][e > 0 ? e - 1 : 0] : nb[r]);
+                out[e] = term_eval<T, C, KIND>(p, iv + e, cur[r][e], n);
+            }
+            T *g = p.G + (o0 + r) * Nw + iv;
+            if (ADD) {
+                T old[VEC];
+                ldg_vec_plain<T, VEC>(old, g);
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) out[e] = add(old[e], out[e]);
+            }
+            stg_vec_stream<T, VEC>(g, out);
+        }
+    }
+}
+
+// Operator along a strided axis (inner > 1): each thread owns VEC consecutive x of R consecutive
+// rows along the operator axis and keeps them in registers, so R outputs cost R+1 row loads.
+template <typename T, typename C, int KIND, bool ADD, int VEC, int R>
+__global__ void __launch_bounds__(256) k_term_s(const __grid_constant__ TermParams<T, C> p) {
+    const int64_t Nw = p.Nw, inner = p.inner;
+    const int64_t x = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    if (x >= inner) return;
+    const int fwd = p.fwd;
+    const T Z = zero_of(T{});
+    for (int64_t o = p.o_begin + blockIdx.z; o < p.o_end; o += gridDim.z) {
+        const T *Fo = p.F + o * Nw * inner + x;
+        for (int64_t i0 = p.i_begin + ((int64_t)blockIdx.y * blockDim.y + threadIdx.y) * R; i0 < p.i_end;
+             i0 += (int64_t)gridDim.y * blockDim.y * R) {
+            // rows i0-1+fwd .. i0+R-1+fwd
+            T V[R + 1][VEC];
+#pragma unroll
+            for (int q = 0; q <= R; ++q) {
+                const int64_t ii = i0 - 1 + fwd + q;
+                const bool needed = (q == 0) || (i0 + q - 1 < p.i_end);  // cur of output row q-… or nb of its neighbour
+                if (needed && ii >= 0 && ii < Nw) ldg_vec_stream<T, VEC>(V[q], Fo + ii * inner);
+                else if (needed && ((ii < 0 && p.bc_lo != BC_SYM) || (ii >= Nw && p.bc_hi != BC_SYM)))
+                    ldg_vec_plain<T, VEC>(V[q], p.ghost + o * p.ghost_stride_o + x);
+                else {
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) V[q][e] = Z;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const int64_t i = i0 + r;
+                if (i >= p.i_end) break;
+                T out[VEC];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    out[e] = term_eval<T, C, KIND>(p, i, fwd ? V[r][e] : V[r + 1][e], fwd ? V[r + 1][e] : V[r][e]);
+                T *g = p.G + (o * Nw + i) * inner + x;
+                if (ADD) {
+                    T old[VEC];
+                    ldg_vec_plain<T, VEC>(old, g);
+#pragma unroll
+                    for (int e = 0; e < VEC; ++e) out[e] = add(old[e], out[e]);
+                }
+                stg_vec_stream<T, VEC>(g, out);
+            }
+        }
+    }
+}
+
 // Gv .= 0   (matrixfree/differential/curl.jl:77) restricted to a contiguous range
 template <typename T>
 __global__ void __launch_bounds__(256) k_fill_zero(T *G, int64_t n) {

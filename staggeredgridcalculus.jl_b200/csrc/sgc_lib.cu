@@ -412,6 +412,54 @@ static int launch_term(const sgc_op *op, const Term &t, T *G, const T *F, const 
     }
     if (p.i_end <= p.i_begin || p.o_end <= p.o_begin) return SGC_OK;
 
+    // ---- vectorised fast path ------------------------------------------------------------------
+    {
+        constexpr int VBIG = 32 / (int)sizeof(T);    // elements in 32 bytes
+        constexpr int VSMALL = 16 / (int)sizeof(T);  // elements in 16 bytes
+        constexpr int R = 4;
+        const bool xax = (p.inner == 1);
+        // (the contiguous-axis kernel reads its ghost element with a scalar load)
+        const bool aligned = ((uintptr_t)p.G % 16 == 0) && ((uintptr_t)p.F % 16 == 0) && (xax || (uintptr_t)p.ghost % 16 == 0);
+        const int64_t len = xax ? p.Nw : p.inner;
+        int vec = 0;
+        if (aligned && len % VBIG == 0) vec = VBIG;
+        else if (aligned && len % VSMALL == 0) vec = VSMALL;
+        const bool full_range = (p.i_begin == 0 && p.i_end == p.Nw);
+        if (vec && op->variant != 3 && (!xax || (full_range && p.Nw >= 64 * vec))) {
+            dim3 vgrid, vblock;
+            if (xax) {
+                vblock = dim3(256, 1, 1);
+                vgrid.x = (unsigned)((p.Nw / vec + 255) / 256);
+                vgrid.y = (unsigned)std::min<int64_t>((p.o_end - p.o_begin + R - 1) / R, 65535);
+                vgrid.z = 1;
+            } else {
+                int bx = 32;
+                while (bx < 256 && bx < p.inner / vec) bx *= 2;
+                const int by = 256 / bx;
+                vblock = dim3(bx, by, 1);
+                vgrid.x = (unsigned)((p.inner / vec + bx - 1) / bx);
+                vgrid.y = (unsigned)std::min<int64_t>((p.i_end - p.i_begin + (int64_t)by * R - 1) / ((int64_t)by * R), 65535);
+                vgrid.z = (unsigned)std::min<int64_t>(p.o_end - p.o_begin, 65535);
+            }
+#define LAUNCH_VEC(KERN, KIND, VEC)                                                            \
+            do {                                                                                \
+                if (add_mode) KERN<T, C, KIND, true, VEC, R><<<vgrid, vblock, 0, st>>>(p);       \
+                else KERN<T, C, KIND, false, VEC, R><<<vgrid, vblock, 0, st>>>(p);               \
+            } while (0)
+#define LAUNCH_VEC_KIND(KERN, VEC)                                                              \
+            switch (t.kind) {                                                                   \
+                case KIND_PARTIAL: LAUNCH_VEC(KERN, KIND_PARTIAL, VEC); break;                  \
+                case KIND_MEAN_ARITH: LAUNCH_VEC(KERN, KIND_MEAN_ARITH, VEC); break;            \
+                default: LAUNCH_VEC(KERN, KIND_MEAN_WEIGHTED, VEC); break;                      \
+            }
+            if (xax) { if (vec == VBIG) { LAUNCH_VEC_KIND(k_term_x, VBIG) } else { LAUNCH_VEC_KIND(k_term_x, VSMALL) } }
+            else     { if (vec == VBIG) { LAUNCH_VEC_KIND(k_term_s, VBIG) } else { LAUNCH_VEC_KIND(k_term_s, VSMALL) } }
+#undef LAUNCH_VEC_KIND
+#undef LAUNCH_VEC
+            return check_launch(xax ? "k_term_x" : "k_term_s");
+        }
+    }
+
     const bool xaxis = (p.inner == 1);
     const int64_t lenx = xaxis ? (p.i_end - p.i_begin) : p.inner;
     int bdx = 32;

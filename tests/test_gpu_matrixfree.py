@@ -67,6 +67,44 @@ def test_apply_partial_complex_everything(S, N):
                 assert_parity(Gd.numpy(), Gref, f"∂ complex N={N} nw={nw} fwd={isfwd} bloch={isbloch} {op}")
 
 
+@pytest.mark.parametrize("N", [(512,), (260, 5), (256, 3, 2), (6, 260), (4, 6, 36), (130, 7, 3), (1024, 2)])
+@pytest.mark.parametrize("cplx", [False, True])
+def test_vectorised_term_kernels_match_oracle_and_scalar_kernel(S, N, cplx):
+    """Sizes that take the vectorised k_term_x / k_term_s kernels (16- and 32-byte vectors, shuffle
+    across the vector boundary, register-marched rows): every kind, axis, direction and boundary,
+    against the oracle and bit-for-bit against the scalar kernel (variant 3)."""
+    rng = np.random.default_rng(150 + len(N) + 3 * cplx)
+    Fu = rand_field(rng, N, cplx)
+    G0 = rand_field(rng, N, cplx)
+    Fd = dev(S, Fu)
+    code = S.SGC_C128 if cplx else S.SGC_F64
+    for nw in range(1, len(N) + 1):
+        n = N[nw - 1]
+        for isfwd, isbloch, op in itertools.product((True, False), (True, False), ("=", "+=")):
+            e = np.exp(-0.4j) if cplx else -1.0
+            alpha = (0.5 + 0.5j) if cplx else 1.25
+            for kind in ("partial", "mhat", "mhat_w"):
+                if kind == "partial":
+                    dwinv = rand_coef(rng, n, cplx)
+                    ref = G0.copy(order="F")
+                    O.apply_partial(ref, Fu, op, nw, isfwd, dwinv, isbloch, e, alpha=alpha)
+                    o = S.Operator.partial(code, N, nw, isfwd, dwinv, isbloch, e, alpha)
+                else:
+                    dw = rand_coef(rng, n, False) if kind == "mhat_w" else None
+                    dwp = rand_coef(rng, n, cplx) if kind == "mhat_w" else None
+                    ref = G0.copy(order="F")
+                    O.apply_mhat(ref, Fu, op, nw, isfwd, dw, dwp, isbloch, e, alpha=alpha)
+                    o = S.Operator.mhat(code, N, nw, isfwd, dw, dwp, isbloch, e, alpha)
+                Ga, Gb = dev(S, G0), dev(S, G0)
+                o.apply(Ga, Fd, op)
+                o.set_tuning(0, 0, 0, 3)
+                o.apply(Gb, Fd, op)
+                what = f"{kind} N={N} nw={nw} fwd={isfwd} bloch={isbloch} {op}"
+                assert_parity(Ga.numpy(), Gb.numpy(), what + " (vector vs scalar)", exact=True)
+                assert_parity(Ga.numpy(), ref, what)
+                o.destroy()
+
+
 def test_apply_partial_errors(S):
     Fu = dev(S, np.zeros((4, 5)))
     with pytest.raises(S.SgcError):  # @assert size(Gv)==size(Fu)          partial.jl:251
