@@ -162,11 +162,12 @@ def run_reference(args, rank, world):
 
 
 def workload_config(n):
-    return {"workload": f"256x256x{256 * n} nonuniform Yee grid, PML-stretched complex dl (Npml=10), PEC outer "
+    fld_mb = NLOCAL[0] * NLOCAL[1] * NLOCAL[2] * 3 * 16 / 1e6
+    return {"workload": f"{NLOCAL[0]}x{NLOCAL[1]}x{NLOCAL[2] * n} nonuniform Yee grid, PML-stretched complex dl (Npml=10), PEC outer "
                         f"boundaries, ComplexF64 curl-of-curl E->H->E' = 2 apply_curl! per step"
-                        + (f", z-slab decomposed over {n} GPUs (256^3 per GPU) with one-plane halos" if n > 1 else ""),
+                        + (f", z-slab decomposed over {n} GPUs ({NLOCAL[0]}x{NLOCAL[1]}x{NLOCAL[2]} per GPU) with one-plane halos" if n > 1 else ""),
             "cells_per_gpu": NLOCAL[0] * NLOCAL[1] * NLOCAL[2], "curl_applies_per_step": 2,
-            "l2_policy": "inputs_larger_than_L2 (3 fields x 805 MB per GPU vs 126 MB L2)",
+            "l2_policy": f"inputs_larger_than_L2 (3 fields x {fld_mb:.0f} MB per GPU vs 126 MB L2)",
             "parallelism": f"zslab{n}"}
 
 
@@ -179,10 +180,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--graph", default="off", choices=["on", "off"])
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--local", default="256,256,256", help="per-GPU slab Nx,Ny,Nz (default: BASELINE configs[1]; 1024,1024,128 = configs[4] at 8 GPUs)")
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    global NLOCAL
+    NLOCAL = tuple(int(v) for v in args.local.split(","))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -359,7 +363,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": workload_config(world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "kernel": "k_curl3p<cplx,cplx,ADD=0,32x4 tile,4-stage cp.async ring>",
+                     "traffic": None, "kernel": "k_curl3p<cplx,cplx,ADD=0,32x4 tile,6-stage cp.async ring>",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * M},

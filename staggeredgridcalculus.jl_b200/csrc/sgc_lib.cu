@@ -540,8 +540,8 @@ static int launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *g
     p.k_begin = (int)k_begin; p.k_end = (int)k_end;
 
     const int kernel_variant = op->variant & 0xF;
-    // defaults from the 256^3 sweep on B200 (profiles/r1_sweep_curl.md): 32x4 tiles, 4-stage ring,
-    // 4 CTAs/SM (128 registers, no spills), 16-plane z-march
+    // defaults from the 256^3 sweeps on B200 (profiles/r1_sweep_curl_256*.jsonl): 32x4 tiles, 6-stage
+    // ring, 4 CTAs/SM (128 registers, no spills), 12-plane z-march
     int tx = op->tile_x ? op->tile_x : 32;
     int ty = op->tile_y ? op->tile_y : (kernel_variant == 1 ? 8 : 4);
     const int64_t gx = (p.Nx + tx - 1) / tx, gy = (p.Ny + ty - 1) / ty;
@@ -553,7 +553,7 @@ static int launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *g
             const int64_t zch = std::max<int64_t>(1, (want + gx * gy - 1) / (gx * gy));
             march = (int)std::max<int64_t>(8, std::min<int64_t>(64, nk / zch));
         } else {
-            march = 16;
+            march = 12;
         }
     }
     p.march = march;
@@ -564,7 +564,8 @@ static int launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *g
         else launch_curl3_tiles<T, C, false>(p, tx, ty, grid, st);
         return check_launch("k_curl3");
     }
-    const int stages = ((op->variant >> 4) & 0xF) ? ((op->variant >> 4) & 0xF) : 4;
+    int stages = (op->variant >> 4) & 0xF;
+    if (!stages) stages = (tx == 32 && ty == 4) ? 6 : 4;  // 6-stage ring: 4 planes in flight per CTA, 47.5 KB, 4 CTAs/SM
     int minb = (op->variant >> 8) & 0xF;
     if (!minb) minb = (tx * ty <= 128) ? 4 : ((tx * ty <= 256) ? 3 : 2);
     const bool xshfl = ((op->variant >> 12) & 1) == 0;  // bit 12: read x-neighbours from the shared tile instead
@@ -595,6 +596,11 @@ static int launch_curl3p_tiles(const CurlParams<T, C> &p, int tx, int ty, int st
         return xshfl ? launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, true>(p, grid, st)                        \
                      : launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, false>(p, grid, st);
     CURLP_CASE(32, 4, 4, 4)
+    CURLP_CASE(32, 4, 5, 4)
+    CURLP_CASE(32, 4, 6, 4)
+    CURLP_CASE(32, 4, 7, 4)
+    CURLP_CASE(32, 4, 8, 3)
+    CURLP_CASE(32, 4, 3, 4)
     CURLP_CASE(32, 8, 3, 3)
     CURLP_CASE(32, 8, 4, 3)
     CURLP_CASE(32, 8, 4, 2)

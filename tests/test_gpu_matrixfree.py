@@ -213,7 +213,7 @@ def test_apply_curl_dtypes_and_alpha(S, cplx_field, cplx_coef, alpha):
 # every instantiated configuration of the fused kernels: (tile_x, tile_y, stages, CTAs/SM) of the
 # cp.async ring kernel (variant 0) with shuffle / shared-memory x-neighbours, and the
 # register-prefetch kernel (variant 1)
-RING_CONFIGS = [(32, 4, 4, 4), (32, 8, 3, 3), (32, 8, 4, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2), (32, 16, 4, 1),
+RING_CONFIGS = [(32, 4, 4, 4), (32, 4, 3, 4), (32, 4, 5, 4), (32, 4, 6, 4), (32, 4, 7, 4), (32, 4, 8, 3), (32, 8, 3, 3), (32, 8, 4, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2), (32, 16, 4, 1),
                 (64, 4, 4, 3), (64, 4, 4, 2), (64, 8, 3, 2)]
 FUSED_VARIANTS = [(tx, ty, 0 | (st << 4) | (mb << 8) | (xs << 12)) for (tx, ty, st, mb) in RING_CONFIGS for xs in (0, 1)]
 FUSED_VARIANTS += [(tx, ty, 1) for (tx, ty) in [(32, 4), (32, 8), (32, 16), (64, 4), (64, 8)]]

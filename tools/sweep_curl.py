@@ -17,7 +17,7 @@ def time_op(o, G, F, op, iters=10, warm=3):
     torch.cuda.synchronize()
     return t0.elapsed_time(t1) / iters
 
-V2 = [(32, 4, 4, 4), (32, 8, 3, 3), (32, 8, 4, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2), (32, 16, 4, 1),
+V2 = [(32, 4, 4, 4), (32, 4, 5, 4), (32, 4, 6, 4), (32, 4, 7, 4), (32, 4, 8, 3), (32, 4, 3, 4), (32, 8, 3, 3), (32, 8, 4, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2), (32, 16, 4, 1),
       (64, 4, 4, 3), (64, 4, 4, 2), (64, 8, 3, 2)]
 
 def main():
