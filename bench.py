@@ -180,13 +180,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--graph", default="off", choices=["on", "off"])
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
-    ap.add_argument("--local", default="256,256,256", help="per-GPU slab Nx,Ny,Nz (default: BASELINE configs[1]; 1024,1024,128 = configs[4] at 8 GPUs)")
+    ap.add_argument("--slab", default="256,256,256", help="per-GPU slab Nx,Ny,Nz (default: BASELINE configs[1]; 1024,1024,128 = configs[4] at 8 GPUs)")
     ap.add_argument("--no-assembly", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="side experiments only: skip the host-array leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     global NLOCAL
-    NLOCAL = tuple(int(v) for v in args.local.split(","))
+    NLOCAL = tuple(int(v) for v in args.slab.split(","))
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -301,48 +302,50 @@ def main():
     value = 2 * M * world / (ms_step * 1e-3) / 1e9  # Gcell-updates/s, whole job
 
     # ---- end-to-end: pinned host arrays → H2D → two curls → D2H, every step ----------------------
-    E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
-    E_host.copy_(E.t)
-    Out_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
-    from sgc_b200._lib import lib, check
-    import ctypes as C
-    st = torch.cuda.current_stream()
     nbytes = 3 * M * 16
+    e2e_val, e2e_s, e2e_steps, e2e_mode = None, 0.0, 1, "skipped (--no-e2e)"
+    if not args.no_e2e:
+        E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+        E_host.copy_(E.t)
+        Out_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+        from sgc_b200._lib import lib, check
+        import ctypes as C
+        st = torch.cuda.current_stream()
 
-    def e2e_step_serial():
-        check(lib.sgc_memcpy_h2d(C.c_void_p(E.ptr), C.c_void_p(E_host.data_ptr()), nbytes, C.c_void_p(st.cuda_stream)))
-        step()
-        check(lib.sgc_memcpy_d2h(C.c_void_p(Out_host.data_ptr()), C.c_void_p(E2.ptr), nbytes, C.c_void_p(st.cuda_stream)))
-        check(lib.sgc_stream_sync(C.c_void_p(st.cuda_stream)))
+        def e2e_step_serial():
+            check(lib.sgc_memcpy_h2d(C.c_void_p(E.ptr), C.c_void_p(E_host.data_ptr()), nbytes, C.c_void_p(st.cuda_stream)))
+            step()
+            check(lib.sgc_memcpy_d2h(C.c_void_p(Out_host.data_ptr()), C.c_void_p(E2.ptr), nbytes, C.c_void_p(st.cuda_stream)))
+            check(lib.sgc_stream_sync(C.c_void_p(st.cuda_stream)))
 
-    e2e_step, e2e_mode = e2e_step_serial, "serial: H2D, 2 curls, D2H"
-    if world == 1:  # z-chunked duplex pipeline (copies in, kernels and copies out overlap)
-        from sgc_b200.hostpipe import HostCurlCurl
-        pipe = HostCurlCurl(c_dual.backend.op, c_prim.backend.op, NLOCAL, nchunks=16)
-        ref_out = None
-        e2e_step_serial()
-        ref_out = Out_host.clone()
-        Out_host.zero_()
-        pipe.run(E_host, Out_host)
-        if not torch.equal(ref_out, Out_host):
-            raise RuntimeError("pipelined host path disagrees with the serial host path")
-        e2e_step = lambda: pipe.run(E_host, Out_host)
-        e2e_mode = "z-chunked (16) full-duplex pipeline: H2D | 2 fused curls per chunk | D2H on three streams"
+        e2e_step, e2e_mode = e2e_step_serial, "serial: H2D, 2 curls, D2H"
+        if world == 1:  # z-chunked duplex pipeline (copies in, kernels and copies out overlap)
+            from sgc_b200.hostpipe import HostCurlCurl
+            pipe = HostCurlCurl(c_dual.backend.op, c_prim.backend.op, NLOCAL, nchunks=16)
+            ref_out = None
+            e2e_step_serial()
+            ref_out = Out_host.clone()
+            Out_host.zero_()
+            pipe.run(E_host, Out_host)
+            if not torch.equal(ref_out, Out_host):
+                raise RuntimeError("pipelined host path disagrees with the serial host path")
+            e2e_step = lambda: pipe.run(E_host, Out_host)
+            e2e_mode = "z-chunked (16) full-duplex pipeline: H2D | 2 fused curls per chunk | D2H on three streams"
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_val = 2 * M * world * e2e_steps / e2e_s / 1e9
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e_val = 2 * M * world * e2e_steps / e2e_s / 1e9
 
     if rank != 0:
         if world > 1:
@@ -368,7 +371,7 @@ def main():
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * M},
         "clocks": clocks,
-        "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+        "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": nbytes if e2e_val else 0, "d2h_bytes_per_step": nbytes if e2e_val else 0,
                 "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps, "mode": e2e_mode},
         "gpu_launches": int(launches),
         "cuda_graph": graph is not None,
@@ -376,7 +379,7 @@ def main():
         "host_enqueue_ms_per_step": host_enqueue_ms,
     }
     tr = os.path.join(ROOT, "profiles", "curl3_traffic.json")
-    if os.path.exists(tr):
+    if os.path.exists(tr) and NLOCAL == (256, 256, 256):  # the capture is of the 256^3 launch
         try:
             out["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
         except Exception:
