@@ -226,14 +226,19 @@ int sgc_asm_set_row_range(sgc_asm *a, int64_t row_begin, int64_t row_end);
  * promote_type of the inputs, curl.jl:59). */
 int sgc_asm_shape(const sgc_asm *a, int64_t *m, int64_t *n, int *val_dtype);
 
-/* Fast path (one pass over the output): sgc_asm_count runs the count pass (per-CTA totals +
- * scan; writes nothing of size O(n)) and returns nnz so that the caller can allocate;
- * sgc_asm_fill_all then writes colptr, rowval and nzval (all DEVICE pointers) in a single
- * kernel — every output byte is written once and nothing of size O(nnz) is read.
- * sgc_asm_count synchronises the stream. */
+/* Fast path (one pass over the output): sgc_asm_count returns nnz so that the caller can
+ * allocate; sgc_asm_fill_all then writes colptr, rowval and nzval (all DEVICE pointers) in a
+ * single kernel — every output byte is written once and nothing of size O(nnz) is read.
+ * When all rows are kept, the number of stored entries per column is separable over the grid
+ * axes, so nnz and every CTA's output offset are closed forms of O(ΣN) prefix tables: no count
+ * kernel, no scan, no synchronisation.  With a row partition sgc_asm_count runs a count pass
+ * (per-CTA totals + device scan) and synchronises the stream. */
 int sgc_asm_count(sgc_asm *a, int64_t *nnz, void *stream);
 int sgc_asm_fill_all(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval,
                      void *stream);
+/* force_count_pass != 0: use the count kernel + device scan even where the closed form applies
+ * (the tests run both and require identical output). */
+int sgc_asm_set_tuning(sgc_asm *a, int force_count_pass);
 
 /* Two-step form with a separate colptr pass (kept for callers that want the structure first).
  * colptr: DEVICE pointer to n+1 Int64.  index_base 1 gives Julia's 1-based arrays, 0 gives

@@ -48,24 +48,51 @@ struct AsmParams {
     int blk_of[3][3];
     int cols_per_group;           // Kin for component-major ordering (a group = one grid cell), else 1
     int64_t ngroups;              // M (component-major) or Kin*M (block ordering: group = (nu, cell))
+    // closed-form entry offsets (all rows kept): the per-column count is separable,
+    // count = a(i) + b(j) + c(k), so the number of entries before a cell is a closed form of the
+    // prefix sums PA, PB, PC.  Set s = nu (block ordering) or 3 (all block columns summed).
+    int prefix_enabled;
+    const int64_t *prefix[4][3];  // [set][axis] → int64[N_axis + 1], exclusive prefix sums
+    int64_t set_base[4];          // entries before the first group of the set
 };
+
+// entries stored before group g (= before its first column) when all rows are kept
+template <typename T, typename IDX>
+SGC_D int64_t prefix_entries_before(const AsmParams<T> &p, int64_t g) {
+    int set = 3;
+    int64_t c = g;
+    if (!(p.cols_per_group > 1 || p.Kin == 1)) {
+        set = (g >= 2 * p.M) ? 2 : (g >= p.M ? 1 : 0);
+        c = g - (int64_t)set * p.M;
+    }
+    const int64_t Nx = p.N[0], Ny = p.N[1];
+    const IDX tq = (IDX)c / (IDX)Nx;  // (32-bit divisions when the matrix is small enough)
+    const int64_t t = (int64_t)tq, i = c - t * Nx, k = (int64_t)(tq / (IDX)Ny), j = t - k * Ny;
+    const int64_t *PA = p.prefix[set][0], *PB = p.prefix[set][1], *PC = p.prefix[set][2];
+    const int64_t SA = PA[Nx], SB = PB[Ny];
+    const int64_t bj = PB[j + 1] - PB[j], ck = PC[k + 1] - PC[k];
+    return p.set_base[set] + k * (Ny * SA + Nx * SB) + Nx * Ny * PC[k]   // whole planes below k
+           + j * SA + Nx * PB[j] + j * Nx * ck                          // whole rows below j in plane k
+           + PA[i] + i * (bj + ck);                                      // cells before i in row (j,k)
+}
 
 SGC_D bool is_zero(double v) { return v == 0.0; }
 SGC_D bool is_zero(cplx v) { return v.re == 0.0 && v.im == 0.0; }
 
 // The (≤ 2) triplets block B contributes to the column of grid cell c: value, LOCAL row of the
 // (block of the) matrix, and validity (nonzero value, row inside the partition).
-template <typename T, typename IDX>
-SGC_D void block_entries(const AsmParams<T> &p, const AsmBlock<T> &B, IDX c, const IDX sub[3], T v[2], int64_t r[2],
+// R is the row-arithmetic type: int32_t when the matrix has fewer than 2^31 rows and columns.
+template <typename T, typename IDX, typename R>
+SGC_D void block_entries(const AsmParams<T> &p, const AsmBlock<T> &B, IDX c, const IDX sub[3], T v[2], R r[2],
                          bool ok[2]) {
     const int a = B.axis;
-    const int64_t Nw = p.N[a];
-    const int64_t cw = (int64_t)sub[a];
-    const int64_t stride = a == 0 ? 1 : (a == 1 ? p.N[0] : p.N[0] * p.N[1]);
+    const R Nw = (R)p.N[a];
+    const R cw = (R)sub[a];
+    const R stride = a == 0 ? (R)1 : (a == 1 ? (R)p.N[0] : (R)(p.N[0] * p.N[1]));
     ok[0] = true;
     ok[1] = false;
-    r[0] = (int64_t)c;
-    r[1] = (int64_t)c;
+    r[0] = (R)c;
+    r[1] = (R)c;
     v[1] = zero_of(T{});
     if (B.ns == 0) {  // diagonal-only (create_πcmp)
         v[0] = B.V0[0];
@@ -74,19 +101,20 @@ SGC_D void block_entries(const AsmParams<T> &p, const AsmBlock<T> &B, IDX c, con
         v[0] = add(B.V0[0], B.Vs[0]);
     } else {
         // off-diagonal triplet of row r lands in column r shifted by +ns  ⇒  r = c − ns
-        int64_t rw = cw - B.ns;
+        R rw = cw - (R)B.ns;
         if (rw < 0) rw += Nw;
         if (rw >= Nw) rw -= Nw;
         v[0] = B.V0[cw];
         v[1] = B.Vs[rw];
-        r[1] = (int64_t)c + (rw - cw) * stride;
+        r[1] = (R)c + (rw - cw) * stride;
         ok[1] = true;
     }
+    const R rb = (R)p.row_begin, re = (R)p.row_end;
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-        const int64_t grow = p.cmpfirst ? (int64_t)p.Kout * r[q] + B.nv : r[q] + p.M * B.nv;
-        ok[q] = ok[q] && !is_zero(v[q]) && grow >= p.row_begin && grow < p.row_end;  // dropzeros!, partition
-        r[q] = grow - p.row_begin;
+        const R grow = p.cmpfirst ? (R)p.Kout * r[q] + (R)B.nv : r[q] + (R)p.M * (R)B.nv;
+        ok[q] = ok[q] && !is_zero(v[q]) && grow >= rb && grow < re;  // dropzeros!, partition
+        r[q] = grow - rb;
     }
 }
 
@@ -132,16 +160,16 @@ SGC_D void group_decode(const AsmParams<T> &p, int64_t g, int &nu0, IDX &c, IDX 
     sub[1] = t - sub[2] * n1;
 }
 
-template <typename T, typename IDX>
+template <typename T, typename IDX, typename R>
 SGC_D int column_count_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3]) {
     int cnt = 0;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
         if (q < p.nblk_of[nu]) {
             T v[2];
-            int64_t r[2];
+            R r[2];
             bool ok[2];
-            block_entries<T, IDX>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
+            block_entries<T, IDX, R>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
             cnt += (int)ok[0] + (int)ok[1];
         }
     }
@@ -179,12 +207,12 @@ SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[
     for (int q = 0; q < E / 2; ++q) {
         if (q < p.nblk_of[nu]) {
             T v[2];
-            int64_t r[2];
+            R r[2];
             bool ok[2];
-            block_entries<T, IDX>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
+            block_entries<T, IDX, R>(p, p.blk[p.blk_of[nu][q]], c, sub, v, r, ok);
             cnt += (int)ok[0] + (int)ok[1];
-            if (ok[0]) { rows[2 * q] = (R)r[0]; vals[2 * q] = v[0]; }
-            if (ok[1]) { rows[2 * q + 1] = (R)r[1]; vals[2 * q + 1] = v[1]; }
+            if (ok[0]) { rows[2 * q] = r[0]; vals[2 * q] = v[0]; }
+            if (ok[1]) { rows[2 * q + 1] = r[1]; vals[2 * q + 1] = v[1]; }
         }
     }
     sort_entries<E>(rows, vals);
@@ -246,7 +274,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
         cnt[q] = 0;
         if (live) {
             if (WRITES) cnt[q] = column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows[WRITES ? q : 0], vals[WRITES ? q : 0]);
-            else cnt[q] = column_count_of<T, IDX>(p, nu0 + q, c, sub);
+            else cnt[q] = column_count_of<T, IDX, R>(p, nu0 + q, c, sub);
         }
         mine += cnt[q];
     }
@@ -258,35 +286,89 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
     }
     // absolute (0-based) position of this CTA's first entry
     const int64_t col0 = g0 * NCOLS;
-    const int64_t base = (MODE == ASM_FILL) ? colptr_in[col0] - p.index_base : cta_offset[blockIdx.x];
+    int64_t base;
+    if (MODE == ASM_FILL) base = colptr_in[col0] - p.index_base;
+    else if (p.prefix_enabled) base = prefix_entries_before<T, IDX>(p, g0);  // closed form: no count pass, no scan
+    else base = cta_offset[blockIdx.x];
+    constexpr int PADK = NCOLS * E;  // entry slots per thread
+    if (total == BLOCK * PADK) {
+        // ---- regular CTA: every column holds exactly E entries (no boundary drop in reach) --------
+        // colptr is an arithmetic sequence; a thread's PADK entries are staged at tid·(PADK+1) + slot
+        // (odd pitch: conflict-free) with compile-time offsets and leave in lane-contiguous stores.
+        const int64_t ib = p.index_base;
+        if (MODE == ASM_COLPTR || MODE == ASM_FILL_ALL) {
+#pragma unroll
+            for (int q = 0; q < NCOLS; ++q) {
+                const int c = threadIdx.x + q * BLOCK;
+                colptr_out[col0 + c] = base + ib + (int64_t)E * c;
+            }
+            if (g == p.ngroups - 1) colptr_out[p.ncol] = base + ib + total;
+            if (MODE == ASM_COLPTR) return;
+        }
+        if (WRITES) {
+            constexpr int SLOTS = BLOCK * (PADK + 1);
+            T *s_vals = reinterpret_cast<T *>(smem_raw);
+            R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)SLOTS);
+            const int s0 = threadIdx.x * (PADK + 1);
+#pragma unroll
+            for (int q = 0; q < NCOLS; ++q)
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    s_rows[s0 + q * E + e] = rows[WRITES ? q : 0][e];
+                    s_vals[s0 + q * E + e] = vals[WRITES ? q : 0][e];
+                }
+            __syncthreads();
+            int64_t *rv = rowval + base + threadIdx.x;
+            T *nz = nzval + base + threadIdx.x;
+#pragma unroll
+            for (int it = 0; it < PADK; ++it) {
+                const int q = threadIdx.x + it * BLOCK;
+                const int slot = q + q / PADK;
+                rv[it * BLOCK] = (int64_t)s_rows[slot] + ib;
+                stg_stream(nz + it * BLOCK, s_vals[slot]);
+            }
+        }
+        return;
+    }
     if (MODE == ASM_COLPTR || MODE == ASM_FILL_ALL) {
+        // colptr of the CTA's columns: staged so that the stores are lane-contiguous
+        __shared__ int64_t s_colptr[BLOCK * NCOLS];
         if (live) {
             int64_t o = base + off0 + p.index_base;
-            const int64_t col = g * NCOLS;
 #pragma unroll
-            for (int q = 0; q < NCOLS; ++q) { colptr_out[col + q] = o; o += cnt[q]; }
+            for (int q = 0; q < NCOLS; ++q) { s_colptr[threadIdx.x * NCOLS + q] = o; o += cnt[q]; }
             if (g == p.ngroups - 1) colptr_out[p.ncol] = o;  // one-past-the-end entry
         }
+        __syncthreads();
+        const int64_t ncols_cta = min((int64_t)BLOCK * NCOLS, p.ncol - col0);
+        for (int q = threadIdx.x; q < ncols_cta; q += BLOCK) colptr_out[col0 + q] = s_colptr[q];
         if (MODE == ASM_COLPTR) return;
     }
     if (WRITES) {
+        // Entry q of the CTA is staged at slot q + q/PADK (the same layout as the regular case)
+        constexpr int SLOTS = BLOCK * (PADK + 1);
         T *s_vals = reinterpret_cast<T *>(smem_raw);
-        R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)BLOCK * NCOLS * E);
+        R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)SLOTS);
         if (live) {
             int o = off0;
 #pragma unroll
             for (int q = 0; q < NCOLS; ++q) {
 #pragma unroll
                 for (int e = 0; e < E; ++e)
-                    if (e < cnt[q]) { s_rows[o + e] = rows[WRITES ? q : 0][e]; s_vals[o + e] = vals[WRITES ? q : 0][e]; }
+                    if (e < cnt[q]) {
+                        const int slot = (o + e) + (o + e) / PADK;
+                        s_rows[slot] = rows[WRITES ? q : 0][e];
+                        s_vals[slot] = vals[WRITES ? q : 0][e];
+                    }
                 o += cnt[q];
             }
         }
         __syncthreads();
         const int64_t ib = p.index_base;
         for (int q = threadIdx.x; q < total; q += BLOCK) {
-            rowval[base + q] = (int64_t)s_rows[q] + ib;
-            stg_stream(nzval + base + q, s_vals[q]);
+            const int slot = q + q / PADK;
+            rowval[base + q] = (int64_t)s_rows[slot] + ib;
+            stg_stream(nzval + base + q, s_vals[slot]);
         }
     }
 }

@@ -1,0 +1,136 @@
+// sgc_curl.cu — launch planning of the fused full 3-D curl kernels (sgc_kernels.cuh: k_curl3p,
+// k_curl3) for apply_curl! (matrixfree/differential/curl.jl:52-137).  Own translation unit so
+// that the many tile / ring-depth instantiations compile in parallel with the rest.
+#include "sgc_internal.h"
+
+#include <algorithm>
+
+#include "sgc_kernels.cuh"
+
+using namespace sgc;
+
+template <typename T, typename C, bool ADD>
+static void launch_curl3_tiles(const CurlParams<T, C> &p, int tx, int ty, dim3 grid_xy_z, cudaStream_t st);
+template <typename T, typename C, bool ADD>
+static int launch_curl3p_tiles(const CurlParams<T, C> &p, int tx, int ty, int stages, int minb, bool xshfl, dim3 grid, cudaStream_t st);
+
+template <typename T, typename C>
+int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghost, bool add_mode,
+                        int64_t k_begin, int64_t k_end, cudaStream_t st) {
+    if (k_end <= k_begin) return SGC_OK;
+    CurlParams<T, C> p{};
+    const int64_t M = op->M, sz = op->N[0] * op->N[1];
+    // per-axis BCs come from the ∂ terms (the term for axis d with the same flags exists twice)
+    int fwd[3] = {0, 0, 0}, bloch[3] = {1, 1, 1};
+    cplx e[3] = {{1, 0}, {1, 0}, {1, 0}};
+    int e_real[3] = {1, 1, 1};
+    for (const Term &t : op->terms)
+        if (t.kind == KIND_PARTIAL) { fwd[t.axis] = t.fwd; bloch[t.axis] = t.bloch; e[t.axis] = t.e; e_real[t.axis] = t.e_real; }
+    for (int d = 0; d < 3; ++d) {
+        p.F[d] = F + d * M;
+        p.G[d] = G + d * M;
+        p.c[d] = (const C *)((const unsigned char *)op->arena + op->fused_off[d]);
+        p.e[d] = e[d]; p.e_real[d] = e_real[d]; p.fwd[d] = fwd[d];
+        p.bc_lo[d] = p.bc_hi[d] = bloch[d] ? BC_BLOCH : BC_SYM;
+    }
+    if (op->lo_iface) p.bc_lo[2] = BC_IFACE;
+    if (op->hi_iface) p.bc_hi[2] = BC_IFACE;
+    for (int c = 0; c < 2; ++c) {
+        const T *g = ghost ? (const T *)ghost[c] : nullptr;
+        p.ghost[c] = g ? g : (fwd[2] ? p.F[c] : p.F[c] + (op->N[2] - 1) * sz);
+    }
+    p.Nx = (int)op->N[0]; p.Ny = (int)op->N[1]; p.Nz = (int)op->N[2];
+    p.k_begin = (int)k_begin; p.k_end = (int)k_end;
+
+    const int kernel_variant = op->variant & 0xF;
+    // defaults from the 256^3 sweeps on B200 (profiles/r1_sweep_curl_256*.jsonl): 32x4 tiles, 6-stage
+    // ring, 4 CTAs/SM (128 registers, no spills), 12-plane z-march
+    int tx = op->tile_x ? op->tile_x : 32;
+    int ty = op->tile_y ? op->tile_y : (kernel_variant == 1 ? 8 : 4);
+    const int64_t gx = (p.Nx + tx - 1) / tx, gy = (p.Ny + ty - 1) / ty;
+    const int64_t nk = k_end - k_begin;
+    int march = op->march;
+    if (march <= 0) {
+        if (kernel_variant == 1) {
+            const int64_t want = 148 * 12;  // ≥ ~4 waves of 3 CTAs/SM
+            const int64_t zch = std::max<int64_t>(1, (want + gx * gy - 1) / (gx * gy));
+            march = (int)std::max<int64_t>(8, std::min<int64_t>(64, nk / zch));
+        } else {
+            march = 12;
+        }
+    }
+    p.march = march;
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)((nk + march - 1) / march));
+    if (grid.y > 65535 || grid.z > 65535) return fail(SGC_ERR_INVALID, "grid too large for the fused curl tiling");
+    if (kernel_variant == 1) {  // v1: register-prefetch z-march
+        if (add_mode) launch_curl3_tiles<T, C, true>(p, tx, ty, grid, st);
+        else launch_curl3_tiles<T, C, false>(p, tx, ty, grid, st);
+        return check_launch("k_curl3");
+    }
+    int stages = (op->variant >> 4) & 0xF;
+    if (!stages) stages = (tx == 32 && ty == 4) ? 6 : 4;  // 6-stage ring: 4 planes in flight per CTA, 47.5 KB, 4 CTAs/SM
+    int minb = (op->variant >> 8) & 0xF;
+    if (!minb) minb = (tx * ty <= 128) ? 4 : ((tx * ty <= 256) ? 3 : 2);
+    const bool xshfl = ((op->variant >> 12) & 1) == 0;  // bit 12: read x-neighbours from the shared tile instead
+    int s = add_mode ? launch_curl3p_tiles<T, C, true>(p, tx, ty, stages, minb, xshfl, grid, st)
+                     : launch_curl3p_tiles<T, C, false>(p, tx, ty, stages, minb, xshfl, grid, st);
+    if (s) return s;
+    return check_launch("k_curl3p");
+}
+
+// v2: cp.async shared-memory ring.
+template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, bool XSHFL>
+static int launch_curl3p_one(const CurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = (size_t)S * 3 * (TY + 1) * (TX + 1) * sizeof(T);
+    auto kern = k_curl3p<T, C, ADD, TX, TY, S, MINB, XSHFL>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
+    return SGC_OK;
+}
+
+template <typename T, typename C, bool ADD>
+static int launch_curl3p_tiles(const CurlParams<T, C> &p, int tx, int ty, int stages, int minb, bool xshfl, dim3 grid, cudaStream_t st) {
+#define CURLP_CASE(TX, TY, S, MINB) \
+    if (tx == TX && ty == TY && stages == S && minb == MINB)                                                   \
+        return xshfl ? launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, true>(p, grid, st)                        \
+                     : launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, false>(p, grid, st);
+    CURLP_CASE(32, 4, 4, 4)
+    CURLP_CASE(32, 4, 5, 4)
+    CURLP_CASE(32, 4, 6, 4)
+    CURLP_CASE(32, 4, 7, 4)
+    CURLP_CASE(32, 4, 8, 3)
+    CURLP_CASE(32, 4, 3, 4)
+    CURLP_CASE(32, 8, 3, 3)
+    CURLP_CASE(32, 8, 4, 3)
+    CURLP_CASE(32, 8, 4, 2)
+    CURLP_CASE(32, 8, 6, 2)
+    CURLP_CASE(32, 16, 3, 2)
+    CURLP_CASE(32, 16, 4, 1)
+    CURLP_CASE(64, 4, 4, 3)
+    CURLP_CASE(64, 4, 4, 2)
+    CURLP_CASE(64, 8, 3, 2)
+#undef CURLP_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl: tile %dx%d, %d stages, %d CTAs/SM is not built", tx, ty, stages, minb);
+}
+
+template <typename T, typename C, bool ADD>
+static void launch_curl3_tiles(const CurlParams<T, C> &p, int tx, int ty, dim3 grid, cudaStream_t st) {
+#define CURL_CASE(TX, TY) \
+    if (tx == TX && ty == TY) { k_curl3<T, C, ADD, TX, TY><<<grid, dim3(TX, TY, 1), 0, st>>>(p); return; }
+    CURL_CASE(32, 4)
+    CURL_CASE(32, 8)
+    CURL_CASE(32, 16)
+    CURL_CASE(64, 4)
+    CURL_CASE(64, 8)
+#undef CURL_CASE
+    k_curl3<T, C, ADD, 32, 8><<<dim3((p.Nx + 31) / 32, (p.Ny + 7) / 8, grid.z), dim3(32, 8, 1), 0, st>>>(p);
+}
+
+
+template int sgc_launch_curl3<double, double>(const sgc_op *, double *, const double *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
+template int sgc_launch_curl3<cplx, double>(const sgc_op *, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
+template int sgc_launch_curl3<cplx, cplx>(const sgc_op *, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);

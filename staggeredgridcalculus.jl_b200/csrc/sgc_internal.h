@@ -88,7 +88,66 @@ struct sgc_asm {
     bool counted = false;
     int *count_tables = nullptr;              // device: A[nu][axis][N_axis] of the separable count
     size_t count_off[3][3] = {};              // element offsets into count_tables
+    int64_t *prefix_tables = nullptr;         // device: exclusive prefix sums of the count tables, sets 0..2 = nu, 3 = all
+    size_t prefix_off[4][3] = {};             // element offsets into prefix_tables
+    int64_t set_total[4] = {0, 0, 0, 0};      // entries of each set when all rows are kept
+    bool force_count_pass = false;            // testing: use the count kernel + device scan even when the closed form applies
     // host convenience
     int64_t *d_colptr = nullptr;
 };
 
+// ---- matrix-free operator handle ----------------------------------------------------------------
+struct Term {
+    int out, in;      // component positions in the last array dimension of G / F
+    int kind;         // KIND_*  or -1 for "Gv .= 0"
+    int axis;         // array dimension (0-based)
+    int fwd, bloch;
+    sgc::cplx e;
+    int e_real;
+    bool cc;          // coefficient tables are complex
+    size_t off_c, off_w;  // offsets of the tables in the arena (bytes); w unused unless weighted
+    sgc::cplx a2, a1, b0, w_hi, w_lo;  // scalars (stored as complex; narrowed when !cc)
+};
+
+struct sgc_op {
+    int dtype = 0, ndim = 0;
+    int64_t N[3] = {1, 1, 1};
+    int64_t M = 1;
+    int n_out = 0, n_in = 0;
+    std::vector<Term> terms;      // in the reference's execution order, grouped by `out`
+    bool fused_curl = false;
+    bool fused_cc = false;
+    size_t fused_off[3] = {0, 0, 0};
+    int fused_pat = -1;           // PAT_* when the term list is one of the one-launch compositions
+    int lo_iface = 0, hi_iface = 0;
+    int tile_x = 0, tile_y = 0, march = 0, variant = 0;
+    void *arena = nullptr;        // device
+    // host-array convenience buffers
+    mutable void *dF = nullptr, *dG = nullptr;
+    mutable cudaStream_t hstream = nullptr;
+};
+
+struct OpBuilder {
+    std::vector<unsigned char> host;
+    size_t push(const std::vector<HV> &v, bool as_complex) {
+        size_t off = (host.size() + 15) & ~size_t(15);
+        size_t bytes = v.size() * (as_complex ? 16 : 8);
+        host.resize(off + bytes);
+        double *d = (double *)(host.data() + off);
+        for (size_t i = 0; i < v.size(); ++i) {
+            if (as_complex) { d[2 * i] = v[i].re; d[2 * i + 1] = v[i].cx ? v[i].im : 0.0; }
+            else d[i] = v[i].re;
+        }
+        return off;
+    }
+};
+
+
+// translation-unit boundaries: the fused 3-D curl lives in sgc_curl.cu (explicitly instantiated
+// for the three (field, coefficient) type pairs), the assembly in sgc_asm.cu
+template <typename T, typename C>
+int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghost, bool add_mode,
+                     int64_t k_begin, int64_t k_end, cudaStream_t st);
+int sgc_check_common(int dtype, int ndim, const int64_t *N);
+#define fail sgc_fail
+#define check_launch sgc_check_launch

@@ -72,11 +72,13 @@ def _finish(a: _Asm, index_base, row_range, method, device, stream=None) -> Devi
     colptr = torch.empty(n.value + 1, dtype=torch.int64, device=dev)
     nnz = C.c_int64()
     st = stream_handle(stream)
-    # count pass (per-CTA totals + scan): returns nnz so that rowval / nzval can be allocated
+    if method == "counted":  # the count kernel + device scan instead of the closed-form offsets
+        check(lib.sgc_asm_set_tuning(a.h, 1))
+    # nnz (closed form, or the count pass for a row partition) so that rowval / nzval can be allocated
     check(lib.sgc_asm_count(a.h, C.byref(nnz), st))
     rowval = torch.empty(nnz.value, dtype=torch.int64, device=dev)
     nzval = torch.empty(nnz.value, dtype=vdt, device=dev)
-    if method == "direct":  # one pass: colptr + rowval + nzval
+    if method in ("direct", "counted"):  # one pass: colptr + rowval + nzval
         check(lib.sgc_asm_fill_all(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.c_void_p(rowval.data_ptr()),
                                    C.c_void_p(nzval.data_ptr()), st))
     elif method == "twostep":  # colptr first, then rowval / nzval from the given colptr

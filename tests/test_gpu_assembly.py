@@ -41,7 +41,7 @@ def test_create_partial_matches_oracle(S, N):
                              (rand_coef(rng, N[nw - 1], True), np.exp(0.8j)),
                              (2.0, -1.0)]:
                 ref = O.create_partial(nw, isfwd, N, dwinv, isbloch, e)
-                for method in ("direct", "twostep", "coo"):
+                for method in ("direct", "counted", "twostep", "coo"):
                     got = S.create_partial(nw, isfwd, N, dwinv, isbloch, e, method=method)
                     assert_csc_equal(got, ref, f"create_∂ N={N} nw={nw} fwd={isfwd} bloch={isbloch} {method}")
 
@@ -84,7 +84,7 @@ def test_create_curl_matches_oracle(S, N, isfwd):
     for dl, isbloch, ee in cases:
         for cmpfirst in (True, False):
             ref = O.create_curl(isfwd, dl, isbloch, ee, N=N if dl is None else None, order_cmpfirst=cmpfirst)
-            for method in ("direct", "twostep", "coo"):
+            for method in ("direct", "counted", "twostep", "coo"):
                 got = S.create_curl(isfwd, dl, isbloch, ee, N=N, order_cmpfirst=cmpfirst, method=method)
                 assert_csc_equal(got, ref, f"create_curl N={N} fwd={isfwd} bloch={isbloch} cmpfirst={cmpfirst} {method}")
 
@@ -117,14 +117,14 @@ def test_create_subcurls_divg_grad_picmp_match_oracle(S):
             ib = ([True, False, False])[:K]
             ee = e[:K]
             for cmpfirst in (True, False):
-                for method in ("direct", "twostep", "coo"):
+                for method in ("direct", "counted", "twostep", "coo"):
                     assert_csc_equal(S.create_divg(fw, dl, ib, ee, order_cmpfirst=cmpfirst, method=method),
                                      O.create_divg(fw, dl, ib, ee, order_cmpfirst=cmpfirst), f"divg K={K} {fw} {method}")
                     assert_csc_equal(S.create_grad(fw, dl, ib, ee, order_cmpfirst=cmpfirst, method=method),
                                      O.create_grad(fw, dl, ib, ee, order_cmpfirst=cmpfirst), f"grad K={K} {fw} {method}")
     for cmpfirst in (True, False):
         for scale in ([-1, 1, -1], [0.5, 0.0, 2.0], [1j, 2.0, -1.0]):
-            for method in ("direct", "twostep", "coo"):
+            for method in ("direct", "counted", "twostep", "coo"):
                 assert_csc_equal(S.create_picmp((3, 4), [3, 1, 2], scale=scale, order_cmpfirst=cmpfirst, method=method),
                                  O.create_picmp((3, 4), [3, 1, 2], scale=scale, order_cmpfirst=cmpfirst),
                                  f"πcmp cmpfirst={cmpfirst} scale={scale} {method}")

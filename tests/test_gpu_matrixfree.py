@@ -328,6 +328,102 @@ def test_apply_divg_grad_match_oracle(S, N):
 
 
 # ------------------------------------------------------------------------------------------------
+# one-launch compositions (k_fused): divg, grad, 2-D TE / TM sub-curls
+# ------------------------------------------------------------------------------------------------
+FUSED_COMPOSITION_SIZES = [(66, 9), (64, 70), (8, 260), (34, 6, 5), (128, 5, 3), (36, 37, 2), (4, 3, 9), (40, 13, 6)]
+
+
+def _compositions(S, N, rng, cplx_field, cplx_coef, isfwd, isbloch, e, alpha):
+    """(name, build-operator, oracle-call, output shape, input shape) for every composition on N."""
+    K = len(N)
+    dt = S.SGC_C128 if cplx_field else S.SGC_F64
+    dlinv = [rand_coef(rng, n, cplx_coef) for n in N]
+    out = [("divg", lambda: S.Operator.divg(dt, N, isfwd, dlinv, isbloch, e, alpha=alpha),
+            lambda G, F, op: O.apply_divg(G, F, op, isfwd, dlinv, isbloch, e, alpha=alpha), N, N + (K,)),
+           ("grad", lambda: S.Operator.grad(dt, N, isfwd, dlinv, isbloch, e, alpha=alpha),
+            lambda G, F, op: O.apply_grad(G, F, op, isfwd, dlinv, isbloch, e, alpha=alpha), N + (K,), N)]
+    if K == 2:
+        for name, shp, co, ci in (("TE", [1, 2], [3], [1, 2]), ("TM", [1, 2], [1, 2], [3]), ("TE'", [2, 1], [3], [2, 1]),
+                                  ("TM'", [3, 1], [3, 1], [2])):
+            out.append((name, lambda shp=shp, co=co, ci=ci: S.Operator.curl(dt, N, isfwd, dlinv, isbloch, e, cmp_shp=shp, cmp_out=co, cmp_in=ci, alpha=alpha),
+                        lambda G, F, op, shp=shp, co=co, ci=ci: O.apply_curl(G, F, op, isfwd, dlinv, isbloch, e, cmp_shp=shp, cmp_out=co, cmp_in=ci, alpha=alpha),
+                        N + (len(co),), N + (len(ci),)))
+    return out
+
+
+@pytest.mark.parametrize("N", FUSED_COMPOSITION_SIZES)
+@pytest.mark.parametrize("cplx_field,cplx_coef", [(False, False), (True, False), (True, True)])
+def test_fused_compositions_match_oracle_and_sweeps(S, N, cplx_field, cplx_coef):
+    """One launch per divergence / gradient / TE / TM curl, bit-identical to the oracle and to the
+    library's own sweep path (variant 2 = the reference's structure), for every direction and
+    boundary combination, `=` and `+=`."""
+    rng = np.random.default_rng(4100 + len(N) + 2 * cplx_field + cplx_coef)
+    K = len(N)
+    fused_seen = 0
+    for isfwd in itertools.product((False, True), repeat=K):
+        for isbloch in ([True] * K, [False] * K, [True, False, True][:K]):
+            e = list(np.exp(-1j * rng.uniform(0, 3, K))) if cplx_field else [1.0, -1.0, 1.0][:K]
+            alpha = (0.75 - 0.5j) if cplx_coef else -1.25
+            for name, build, oracle, gshape, fshape in _compositions(S, N, rng, cplx_field, cplx_coef, list(isfwd), isbloch, e, alpha):
+                F = rand_field(rng, fshape, cplx_field)
+                G0 = rand_field(rng, gshape, cplx_field)
+                o = build()
+                for op in ("=", "+="):
+                    Gref = G0.copy(order="F")
+                    oracle(Gref, F, op)
+                    Ga, Gb = dev(S, G0), dev(S, G0)
+                    o.set_tuning(0, 0, 0, 0)
+                    n0 = S.launch_count()
+                    o.apply(Ga, dev(S, F), op)
+                    fused_seen += (S.launch_count() - n0 == 1)
+                    o.set_tuning(0, 0, 0, 2)
+                    o.apply(Gb, dev(S, F), op)
+                    what = f"{name} N={N} fwd={isfwd} bloch={isbloch} {op}"
+                    assert_parity(Ga.numpy(), Gref, what + " (fused vs oracle)", exact=True)
+                    assert_parity(Ga.numpy(), Gb.numpy(), what + " (fused vs sweeps)", exact=True)
+                o.destroy()
+    assert fused_seen > 0, "the one-launch path never ran"
+
+
+def test_fused_divg_grad_slab_split_equals_whole(S):
+    """z-slab interfaces (ghost planes) through the fused divergence / gradient kernels."""
+    rng = np.random.default_rng(4200)
+    N, ks = (18, 7, 9), 4
+    dlinv = [rand_coef(rng, n, True) for n in N]
+    plane = N[0] * N[1] * 16
+    for isfwd_z, isbloch_z in itertools.product((True, False), repeat=2):
+        isfwd, isbloch, e = [False, True, isfwd_z], [True, False, isbloch_z], [np.exp(0.4j), 1.0, np.exp(-1.1j)]
+        for kind, fshape, gshape in (("divg", N + (3,), N), ("grad", N, N + (3,))):
+            F, G0 = rand_field(rng, fshape, True), rand_field(rng, gshape, True)
+            mk = getattr(S.Operator, kind)
+            whole = mk(S.SGC_C128, N, isfwd, dlinv, isbloch, e)
+            Gw = dev(S, G0)
+            whole.apply(Gw, dev(S, F), "+=")
+            ref, out = Gw.numpy(), np.empty_like(G0)
+            slabs = [(0, ks), (ks, N[2])]
+            cut = lambda A, a, b: np.asfortranarray(A[:, :, a:b] if A.ndim == 3 else A[:, :, a:b, :])
+            Fd = [dev(S, cut(F, a, b)) for a, b in slabs]
+            for r, (a, b) in enumerate(slabs):
+                Nl = (N[0], N[1], b - a)
+                o = mk(S.SGC_C128, Nl, isfwd, [dlinv[0], dlinv[1], dlinv[2][a:b]], isbloch, e)
+                o.set_slab(lo_interface=(r == 1), hi_interface=(r == 0))
+                other, No = Fd[1 - r], slabs[1 - r][1] - slabs[1 - r][0]
+                kpl = 0 if isfwd_z else No - 1
+                ncomp = 3 if kind == "divg" else 1
+                ghost = [(other.component(c + 1).ptr if other.ndim == 4 else other.ptr) + kpl * plane for c in range(ncomp)]
+                Gd = dev(S, cut(G0, a, b))
+                kb = (b - a - 1) if isfwd_z else 0
+                for k0, k1 in ((0, kb), (kb, kb + 1), (kb + 1, b - a)):
+                    o.apply_range(Gd, Fd[r], "+=", k0, k1, ghost)
+                if out.ndim == 3:
+                    out[:, :, a:b] = Gd.numpy()
+                else:
+                    out[:, :, a:b, :] = Gd.numpy()
+                o.destroy()
+            assert_parity(out, ref, f"fused {kind} slab split fwd_z={isfwd_z} bloch_z={isbloch_z}", exact=True)
+
+
+# ------------------------------------------------------------------------------------------------
 # z-slab mode on one GPU: two slabs with ghost planes reproduce the undivided result
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("isfwd_z,isbloch_z", [(True, True), (False, True), (True, False), (False, False)])

@@ -40,7 +40,7 @@ def run(n, cplx, isbloch, cmpfirst=1):
     lib.sgc_asm_destroy(h)
 
 if __name__ == "__main__":
-    for n in (256, 512):
+    for n in ([int(a) for a in sys.argv[1:]] or [256, 512]):
         run(n, False, [1, 1, 1])
         run(n, True, [1, 1, 1])
         run(n, False, [1, 0, 0])
