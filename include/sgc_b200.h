@@ -174,6 +174,26 @@ int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int ndim, cons
                    int coef_complex, const int *isbloch, const double *e, const double *alpha,
                    void *stream);
 
+/* Fused curl-of-curl  G OP C2(C1 F)  in one pass over memory: the intermediate field
+ * H = C1 F stays in shared memory (96 instead of 192 bytes per ComplexF64 cell).  Bit-identical
+ * to sgc_op_apply(c1, H, F, SET) followed by sgc_op_apply(c2, G, H, opmode); replaces the pair
+ * of apply_curl! calls either side of H in a Maxwell solve (matrixfree/differential/curl.jl:52-137
+ * twice; matrix form `Cv*Cu`, test/curl.jl:123-153).  c1, c2: full 3-D curl operators on the same
+ * grid, field type and coefficient type.  Tuning is taken from c2 (tile_x, tile_y, march_z,
+ * variant bits 4-7 = E-ring stages). */
+int sgc_op_apply_curlcurl(const sgc_op *c2, const sgc_op *c1, void *G, const void *F, int opmode,
+                          void *stream);
+/* z-slab form: planes [k_begin,k_end); at an interface (sgc_op_set_slab on BOTH operators)
+ * ghost_lo[c] / ghost_hi[c] are DEVICE (or peer) pointers to plane -1 / plane Nz of input
+ * component c (all three components, whole planes), and sgc_op_set_slab_coef(c1, ...) must have
+ * supplied the neighbours' dz^-1 entries.  Needs opposite z-directions in c1 and c2. */
+int sgc_op_apply_curlcurl_range(const sgc_op *c2, const sgc_op *c1, void *G, const void *F, int opmode,
+                                const void *const *ghost_lo, const void *const *ghost_hi,
+                                int64_t k_begin, int64_t k_end, void *stream);
+/* dz^-1 of the plane below the slab (global plane k0-1) and above it (global plane k1), one
+ * element each (re[,im]); NULL = 1.0.  Stored pre-multiplied by alpha like the tables. */
+int sgc_op_set_slab_coef(sgc_op *op, const double *dzinv_below, const double *dzinv_above, int coef_complex);
+
 /* Host-array convenience (strict drop-in for Julia `Array`s; PCIe-bound): copies F (and G for
  * SGC_OP_ADD) to the device, applies, copies G back, synchronises.  `G_host`/`F_host` hold
  * n_out / n_in components of prod(N) elements each. */

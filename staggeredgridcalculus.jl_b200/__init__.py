@@ -8,7 +8,8 @@ in-tree CUDA library `csrc/libsgc_b200.so` — there is no CPU fallback.
 from . import _lib
 from ._lib import SgcError, InexactError, SGC_F64, SGC_C128, LIB_PATH
 from .device import DeviceArray
-from .matrixfree import (Operator, apply_partial, apply_mhat, apply_curl, apply_divg, apply_grad, apply_mean)
+from .matrixfree import (Operator, apply_partial, apply_mhat, apply_curl, apply_curlcurl, apply_divg, apply_grad,
+                         apply_mean)
 from .matrix import (DeviceCSC, create_partial, create_mhat, create_mean, create_curl, create_divg, create_grad,
                      create_picmp)
 from . import gridgen

@@ -83,6 +83,10 @@ _PROTOS = {
                                  intp, dblp, dblp, C.c_void_p]),
     "sgc_apply_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, i64p, intp, vpp, vpp,
                                  C.c_int, intp, dblp, dblp, C.c_void_p]),
+    "sgc_op_apply_curlcurl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "sgc_op_apply_curlcurl_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, vpp,
+                                              C.c_int64, C.c_int64, C.c_void_p]),
+    "sgc_op_set_slab_coef": (C.c_int, [C.c_void_p, dblp, dblp, C.c_int]),
     "sgc_op_apply_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "sgc_asm_create_partial": (C.c_int, [vpp, C.c_int, i64p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, dblp,
                                          C.c_int]),

@@ -1,0 +1,147 @@
+// sgc_curlcurl.cu — launch planning and C-ABI entry points of the fused curl-of-curl
+// (sgc_curlcurl.cuh): G OP C₂(C₁ F) in one pass, H never written to memory.
+#include "sgc_internal.h"
+
+#include <algorithm>
+
+#include "sgc_curlcurl.cuh"
+
+using namespace sgc;
+
+namespace {
+
+template <typename T, typename C, bool ADD, int TX, int TY, int SE, int MINB>
+int launch_cc_one(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = ((size_t)SE * 3 * (TX + 2) * (TY + 2) + (size_t)3 * 3 * (TX + 1) * (TY + 1)) * sizeof(T);
+    auto kern = k_curlcurl3<T, C, ADD, TX, TY, SE, MINB>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
+    return SGC_OK;
+}
+
+template <typename T, typename C, bool ADD>
+int launch_cc_tiles(const CurlCurlParams<T, C> &p, int tx, int ty, int se, dim3 grid, cudaStream_t st) {
+#define CC_CASE(TX, TY, SE, MINB) \
+    if (tx == TX && ty == TY && se == SE) return launch_cc_one<T, C, ADD, TX, TY, SE, MINB>(p, grid, st);
+    CC_CASE(32, 8, 4, 2)
+    CC_CASE(32, 8, 3, 2)
+    CC_CASE(32, 8, 5, 1)
+    CC_CASE(32, 4, 4, 3)
+    CC_CASE(32, 4, 3, 4)
+    CC_CASE(32, 16, 3, 1)
+    CC_CASE(64, 4, 4, 2)
+    CC_CASE(64, 4, 3, 2)
+#undef CC_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl: tile %dx%d with %d stages is not built", tx, ty, se);
+}
+
+struct AxisInfo {
+    int fwd[3], bloch[3], e_real[3];
+    cplx e[3];
+};
+AxisInfo axis_info(const sgc_op *op) {
+    AxisInfo a{};
+    for (int d = 0; d < 3; ++d) { a.fwd[d] = 0; a.bloch[d] = 1; a.e[d] = cplx{1, 0}; a.e_real[d] = 1; }
+    for (const Term &t : op->terms)
+        if (t.kind == KIND_PARTIAL) { a.fwd[t.axis] = t.fwd; a.bloch[t.axis] = t.bloch; a.e[t.axis] = t.e; a.e_real[t.axis] = t.e_real; }
+    return a;
+}
+
+template <typename C> C narrow_c(cplx v);
+template <> double narrow_c<double>(cplx v) { return v.re; }
+template <> cplx narrow_c<cplx>(cplx v) { return v; }
+
+template <typename T, typename C>
+int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mode, const void *const *ghost_lo,
+              const void *const *ghost_hi, int64_t k_begin, int64_t k_end, cudaStream_t st) {
+    if (k_end <= k_begin) return SGC_OK;
+    CurlCurlParams<T, C> p{};
+    const int64_t M = c1->M;
+    const AxisInfo a1 = axis_info(c1), a2 = axis_info(c2);
+    for (int d = 0; d < 3; ++d) {
+        p.F[d] = F + d * M;
+        p.G[d] = G + d * M;
+        p.c1[d] = (const C *)((const unsigned char *)c1->arena + c1->fused_off[d]);
+        p.c2[d] = (const C *)((const unsigned char *)c2->arena + c2->fused_off[d]);
+        p.e1[d] = a1.e[d]; p.e1_real[d] = a1.e_real[d]; p.fwd1[d] = a1.fwd[d];
+        p.e2[d] = a2.e[d]; p.e2_real[d] = a2.e_real[d]; p.fwd2[d] = a2.fwd[d];
+        p.bc1_lo[d] = p.bc1_hi[d] = a1.bloch[d] ? BC_BLOCH : BC_SYM;
+        p.bc2_lo[d] = p.bc2_hi[d] = a2.bloch[d] ? BC_BLOCH : BC_SYM;
+        p.ghost_lo[d] = ghost_lo ? (const T *)ghost_lo[d] : nullptr;
+        p.ghost_hi[d] = ghost_hi ? (const T *)ghost_hi[d] : nullptr;
+    }
+    if (c1->lo_iface) { p.bc1_lo[2] = BC_IFACE; p.bc2_lo[2] = BC_IFACE; }
+    if (c1->hi_iface) { p.bc1_hi[2] = BC_IFACE; p.bc2_hi[2] = BC_IFACE; }
+    p.c1z_lo = narrow_c<C>(c1->cz_ghost[0]);
+    p.c1z_hi = narrow_c<C>(c1->cz_ghost[1]);
+    p.Nx = (int)c1->N[0]; p.Ny = (int)c1->N[1]; p.Nz = (int)c1->N[2];
+    p.k_begin = (int)k_begin; p.k_end = (int)k_end;
+    // defaults from the 256^3 sweep on B200 (profiles/): 32x8 tile, 4-stage E ring, 2 CTAs/SM
+    const int tx = c2->tile_x ? c2->tile_x : 32;
+    const int ty = c2->tile_y ? c2->tile_y : 8;
+    const int se = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 4;
+    p.march = c2->march > 0 ? c2->march : 32;
+    const int64_t nk = k_end - k_begin;
+    dim3 grid((unsigned)((p.Nx + tx - 1) / tx), (unsigned)((p.Ny + ty - 1) / ty), (unsigned)((nk + p.march - 1) / p.march));
+    if (grid.y > 65535 || grid.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
+    int s = add_mode ? launch_cc_tiles<T, C, true>(p, tx, ty, se, grid, st) : launch_cc_tiles<T, C, false>(p, tx, ty, se, grid, st);
+    if (s) return s;
+    return sgc_check_launch("k_curlcurl3");
+}
+
+}  // namespace
+
+extern "C" int sgc_op_set_slab_coef(sgc_op *op, const double *dzinv_below, const double *dzinv_above, int coef_complex) {
+    REQUIRE(op, "op is NULL");
+    REQUIRE(op->fused_curl, "slab coefficients apply to full 3-D curl operators");
+    const void *v[2] = {dzinv_below, dzinv_above};
+    for (int s = 0; s < 2; ++s) {
+        HV d = v[s] ? vec_at(v[s], coef_complex, 0) : hv(1.0);
+        HV c = hmul(op->alpha, d);  // (α * ∆z⁻¹) exactly as the tables
+        if (c.cx && !op->fused_cc) return sgc_fail(SGC_ERR_INVALID, "complex ghost coefficient for an operator with real tables");
+        op->cz_ghost[s] = to_cplx(c);
+    }
+    return SGC_OK;
+}
+
+extern "C" int sgc_op_apply_curlcurl_range(const sgc_op *c2, const sgc_op *c1, void *G, const void *F, int opmode,
+                                           const void *const *ghost_lo, const void *const *ghost_hi,
+                                           int64_t k_begin, int64_t k_end, void *stream) {
+    REQUIRE(c1 && c2 && G && F, "NULL argument");
+    REQUIRE(opmode == SGC_OP_SET || opmode == SGC_OP_ADD, "opmode must be SGC_OP_SET or SGC_OP_ADD");
+    REQUIRE(c1->fused_curl && c2->fused_curl, "the fused curl-of-curl needs two full 3-D curl operators");
+    REQUIRE(c1->dtype == c2->dtype, "the two curls must have the same field type");
+    for (int d = 0; d < 3; ++d) REQUIRE(c1->N[d] == c2->N[d], "the two curls must act on the same grid");
+    REQUIRE(c1->fused_cc == c2->fused_cc, "the two curls must both have real or both have complex coefficient tables");
+    REQUIRE(c1->lo_iface == c2->lo_iface && c1->hi_iface == c2->hi_iface, "the two curls must share the slab interfaces");
+    REQUIRE(0 <= k_begin && k_begin <= k_end && k_end <= c1->N[2], "plane range [%lld,%lld) outside 0..%lld",
+            (long long)k_begin, (long long)k_end, (long long)c1->N[2]);
+    REQUIRE(G != F, "G and F must not alias");
+    const bool any_ghost = (ghost_lo && ghost_lo[0]) || (ghost_hi && ghost_hi[0]);
+    if (ghost_lo && ghost_lo[0]) REQUIRE(ghost_lo[1] && ghost_lo[2], "ghost_lo needs all three components");
+    if (ghost_hi && ghost_hi[0]) REQUIRE(ghost_hi[1] && ghost_hi[2], "ghost_hi needs all three components");
+    if (c1->lo_iface || c1->hi_iface || any_ghost) {
+        int fz1 = 0, fz2 = 0;
+        for (const Term &t : c1->terms) if (t.kind == KIND_PARTIAL && t.axis == 2) fz1 = t.fwd;
+        for (const Term &t : c2->terms) if (t.kind == KIND_PARTIAL && t.axis == 2) fz2 = t.fwd;
+        REQUIRE(fz1 != fz2, "slab interfaces need opposite z-directions in the two curls (halo reach of one plane)");
+        if (c1->lo_iface) REQUIRE(ghost_lo && ghost_lo[0] && ghost_lo[1] && ghost_lo[2], "ghost_lo planes are required at a lower interface");
+        if (c1->hi_iface) REQUIRE(ghost_hi && ghost_hi[0] && ghost_hi[1] && ghost_hi[2], "ghost_hi planes are required at an upper interface");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool add = opmode == SGC_OP_ADD;
+    if (c1->dtype == SGC_F64)
+        return launch_cc<double, double>(c2, c1, (double *)G, (const double *)F, add, ghost_lo, ghost_hi, k_begin, k_end, st);
+    if (c1->fused_cc)
+        return launch_cc<cplx, cplx>(c2, c1, (cplx *)G, (const cplx *)F, add, ghost_lo, ghost_hi, k_begin, k_end, st);
+    return launch_cc<cplx, double>(c2, c1, (cplx *)G, (const cplx *)F, add, ghost_lo, ghost_hi, k_begin, k_end, st);
+}
+
+extern "C" int sgc_op_apply_curlcurl(const sgc_op *c2, const sgc_op *c1, void *G, const void *F, int opmode, void *stream) {
+    REQUIRE(c1 && c2, "NULL argument");
+    return sgc_op_apply_curlcurl_range(c2, c1, G, F, opmode, nullptr, nullptr, 0, c1->N[2], stream);
+}

@@ -120,6 +120,8 @@ struct sgc_op {
     size_t fused_off[3] = {0, 0, 0};
     int fused_pat = -1;           // PAT_* when the term list is one of the one-launch compositions
     int lo_iface = 0, hi_iface = 0;
+    HV alpha = {1.0, 0.0, false};                    // α of a curl operator (for the ghost-plane coefficients)
+    sgc::cplx cz_ghost[2] = {{1.0, 0.0}, {1.0, 0.0}};  // α·∆z⁻¹ of the planes −1 / Nz (slab neighbours)
     int tile_x = 0, tile_y = 0, march = 0, variant = 0;
     void *arena = nullptr;        // device
     // host-array convenience buffers

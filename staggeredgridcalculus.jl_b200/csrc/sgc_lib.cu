@@ -281,6 +281,7 @@ extern "C" int sgc_op_create_curl(sgc_op **op_out, int dtype, int ndim, const in
     for (int d = 0; d < 3 && full; ++d) full = cmp_shp[d] == d + 1 && cmp_out[d] == d + 1 && cmp_in[d] == d + 1;
     if (full) {
         op->fused_curl = true;
+        op->alpha = al;
         op->fused_cc = al.cx || coef_complex;
         for (int d = 0; d < 3; ++d) {
             std::vector<HV> c(op->N[d]);
@@ -511,7 +512,29 @@ static bool launch_fused_sweep(const FusedParams<T, C> &p, int vecbytes, int row
 }
 #endif
 
-// returns 1 when the call cannot take the fused path (caller falls back to the sweeps)
+// (vector bytes, rows per thread, CTAs/SM) per composition from the B200 sweep
+// (profiles/r1_sweep_fused.jsonl): 16-byte vectors and 3-4 resident CTAs win almost everywhere; the
+// Float64 two-input compositions prefer 32-byte vectors of a single row.
+template <typename T, typename C, int P, int VB, int RR, int MB>
+static void launch_fused_cfg(const FusedParams<T, C> &p, bool add_mode, cudaStream_t st) {
+    if (add_mode) launch_fused_one<T, C, P, true, VB / (int)sizeof(T), RR, MB>(p, st);
+    else launch_fused_one<T, C, P, false, VB / (int)sizeof(T), RR, MB>(p, st);
+}
+template <typename T, typename C, int P>
+static void launch_fused_pat(const FusedParams<T, C> &p, bool add_mode, cudaStream_t st) {
+    if constexpr (P == PAT_GATHER_XYZ || P == PAT_SCATTER_XYZ) {
+        launch_fused_cfg<T, C, P, 16, 2, 4>(p, add_mode, st);
+    } else if constexpr (sizeof(T) == 16) {
+        launch_fused_cfg<T, C, P, 16, 4, 2>(p, add_mode, st);
+    } else if constexpr (P == PAT_GATHER_XY || P == PAT_GATHER_YX) {
+        if (p.Nx % 4 == 0) launch_fused_cfg<T, C, P, 32, 1, 4>(p, add_mode, st);
+        else launch_fused_cfg<T, C, P, 16, 4, 3>(p, add_mode, st);
+    } else {
+        launch_fused_cfg<T, C, P, 16, 4, 3>(p, add_mode, st);
+    }
+}
+
+// *done = false when the call cannot take the fused path (caller falls back to the sweeps)
 template <typename T, typename C>
 static int launch_fused(const sgc_op *op, T *G, const T *F, const void *const *ghost, bool add_mode,
                         int64_t k_begin, int64_t k_end, cudaStream_t st, bool *done) {
@@ -549,20 +572,30 @@ static int launch_fused(const sgc_op *op, T *G, const T *F, const void *const *g
     // (vector bytes, rows per thread, CTAs/SM) per composition from the B200 sweep
     // (profiles/r1_sweep_fused.jsonl): 16-byte vectors and 3-4 resident CTAs win almost everywhere;
     // the Float64 two-input compositions prefer 32-byte vectors of a single row.
-#define FUSED_GO(P, VB, RR, MB)                                                                          \
-    do {                                                                                                \
-        if (add_mode) launch_fused_one<T, C, P, true, VB / (int)sizeof(T), RR, MB>(p, st);               \
-        else launch_fused_one<T, C, P, false, VB / (int)sizeof(T), RR, MB>(p, st);                       \
-    } while (0)
-#define FUSED_CASE(P)                                                                                   \
-    case P:                                                                                             \
-        if (P == PAT_GATHER_XYZ || P == PAT_SCATTER_XYZ) FUSED_GO(P, 16, 2, 4);                          \
-        else if (sizeof(T) == 16) FUSED_GO(P, 16, 4, 2);                                                 \
-        else if ((P == PAT_GATHER_XY || P == PAT_GATHER_YX) && op->N[0] % 4 == 0) FUSED_GO(P, 32, 1, 4); \
-        else FUSED_GO(P, 16, 4, 3);                                                                      \
-        break;
-#undef FUSED_CASE
-#undef FUSED_GO
+#ifdef SGC_FUSED_SWEEP
+    if (op->tile_x && !add_mode) {
+        bool ok = false;
+        switch (op->fused_pat) {
+            case 1: ok = launch_fused_sweep<T, C, 1>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 2: ok = launch_fused_sweep<T, C, 2>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 4: ok = launch_fused_sweep<T, C, 4>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 5: ok = launch_fused_sweep<T, C, 5>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            default: break;
+        }
+        if (!ok) return fail(SGC_ERR_INVALID, "fused sweep: configuration not built");
+        *done = true;
+        return check_launch("k_fused");
+    }
+#endif
+    switch (op->fused_pat) {
+        case 0: launch_fused_pat<T, C, 0>(p, add_mode, st); break;
+        case 1: launch_fused_pat<T, C, 1>(p, add_mode, st); break;
+        case 2: launch_fused_pat<T, C, 2>(p, add_mode, st); break;
+        case 3: launch_fused_pat<T, C, 3>(p, add_mode, st); break;
+        case 4: launch_fused_pat<T, C, 4>(p, add_mode, st); break;
+        case 5: launch_fused_pat<T, C, 5>(p, add_mode, st); break;
+        default: return SGC_OK;
+    }
     *done = true;
     return check_launch("k_fused");
 }

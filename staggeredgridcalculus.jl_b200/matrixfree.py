@@ -151,6 +151,36 @@ class Operator:
         check(lib.sgc_op_apply_range(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr,
                                      int(k_begin), int(k_end), stream_handle(stream)))
 
+    def apply_after(self, first: "Operator", G: DeviceArray, F: DeviceArray, op="=", k_begin=None, k_end=None,
+                    ghost_lo=None, ghost_hi=None, stream=None):
+        """Fused curl-of-curl `G OP self(first(F))` in one pass over memory (the intermediate field
+        never leaves shared memory); bit-identical to `first.apply(H, F, "=")` followed by
+        `self.apply(G, H, op)`.  Both must be full 3-D curl operators on the same grid.  With slab
+        interfaces, `ghost_lo[c]` / `ghost_hi[c]` are device pointers (ints) of plane −1 / plane Nz
+        of input component c."""
+        first._check_arrays(F, F)
+        self._check_arrays(G, G)
+        Nz = self.N[-1]
+        k_begin = 0 if k_begin is None else int(k_begin)
+        k_end = Nz if k_end is None else int(k_end)
+        glo = None if ghost_lo is None else (C.c_void_p * 3)(*[None if g is None else int(g) for g in ghost_lo])
+        ghi = None if ghost_hi is None else (C.c_void_p * 3)(*[None if g is None else int(g) for g in ghost_hi])
+        check(lib.sgc_op_apply_curlcurl_range(self._h, first._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), glo, ghi,
+                                              k_begin, k_end, stream_handle(stream)))
+
+    def set_slab_coef(self, dzinv_below=None, dzinv_above=None):
+        """∆z⁻¹ of the planes just below / above this rank's slab (the neighbours' entries), needed by
+        the fused curl-of-curl at slab interfaces."""
+        vals = [v for v in (dzinv_below, dzinv_above) if v is not None]
+        cc = int(any(np.iscomplexobj(np.asarray(v)) for v in vals))
+        def pack(v):
+            if v is None:
+                return None
+            z = complex(v)
+            return (C.c_double * 2)(z.real, z.imag) if cc else (C.c_double * 1)(float(np.real(v)))
+        a, b = pack(dzinv_below), pack(dzinv_above)
+        check(lib.sgc_op_set_slab_coef(self._h, a, b, cc))
+
     def apply_host(self, G: np.ndarray, F: np.ndarray, op="="):
         """Host arrays in, host arrays out (column-major numpy arrays, modified in place)."""
         assert G.flags.f_contiguous and F.flags.f_contiguous
@@ -225,6 +255,22 @@ def apply_curl(G: DeviceArray, F: DeviceArray, op, isfwd, dlinv=None, isbloch=No
     o = Operator.curl(F.dtype_code, G.shape[:K], isfwd, dlinv, isbloch, e, cmp_shp, cmp_out, cmp_in, alpha)
     o.apply(G, F, op, stream)
     _sync_and_destroy(o, stream)
+    return None
+
+
+def apply_curlcurl(G: DeviceArray, F: DeviceArray, op, isfwd1, dlinv1, isfwd2, dlinv2, isbloch=None, e=None, *,
+                   alpha1=1.0, alpha2=1.0, stream=None):
+    """`G OP ∇₂×(∇₁×F)`: the pair `apply_curl!(H, F, Val(:(=)), isfwd1, ∆l₁⁻¹, …)`,
+    `apply_curl!(G, H, Val(OP), isfwd2, ∆l₂⁻¹, …)` (matrixfree/differential/curl.jl:52-137 twice) in
+    one pass over memory, H never materialised; results are bit-identical to the two calls."""
+    if G.shape != F.shape or G.ndim != 4 or G.shape[3] != 3:
+        raise _lib.SgcError(_lib.SGC_ERR_INVALID, f"G {G.shape} / F {F.shape} are not 3-component fields on one 3-D grid")
+    N = G.shape[:3]
+    c1 = Operator.curl(F.dtype_code, N, isfwd1, dlinv1, isbloch, e, alpha=alpha1)
+    c2 = Operator.curl(F.dtype_code, N, isfwd2, dlinv2, isbloch, e, alpha=alpha2)
+    c2.apply_after(c1, G, F, op, stream=stream)
+    _sync_and_destroy(c1, stream)
+    c2.destroy()
     return None
 
 

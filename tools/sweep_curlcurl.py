@@ -1,0 +1,43 @@
+"""Fused curl-of-curl vs two fused curls at 256^3 ComplexF64 (development sweep)."""
+import sys, os, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import sgc_b200 as S
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+N = (n, n, n); M = n ** 3
+gen = torch.Generator(device="cuda").manual_seed(0)
+def rnd():
+    return S.DeviceArray(torch.complex(torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) - 0.5,
+                                       torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) - 0.5), N + (3,))
+E, H, G, Gref = rnd(), S.DeviceArray.zeros(N + (3,)), S.DeviceArray.zeros(N + (3,)), S.DeviceArray.zeros(N + (3,))
+rng = np.random.default_rng(0)
+d1 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for _ in range(3)]
+d2 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for _ in range(3)]
+for bl in ([False] * 3, [True] * 3):
+    c1 = S.Operator.curl(S.SGC_C128, N, [True] * 3, d1, bl, [np.exp(-0.3j)] * 3)
+    c2 = S.Operator.curl(S.SGC_C128, N, [False] * 3, d2, bl, [np.exp(-0.3j)] * 3)
+    def two():
+        c1.apply(H, E, "="); c2.apply(Gref, H, "=")
+    ms2 = timeit(two)
+    print(json.dumps(dict(bloch=bl[0], mode="two fused curls", ms=round(ms2, 4), gcell_pairs=round(M / ms2 / 1e6, 2), gbs_192=round(192 * M / ms2 / 1e6))), flush=True)
+    for tx, ty, se in ((32, 8, 4), (32, 8, 3), (32, 8, 5), (32, 4, 4), (32, 4, 3), (32, 16, 3), (64, 4, 4), (64, 4, 3)):
+        for march in (16, 32, 64):
+            c2.set_tuning(tx, ty, march, se << 4)
+            try:
+                ms = timeit(lambda: c2.apply_after(c1, G, E, "="))
+                ok = bool(torch.equal(torch.view_as_real(G.t), torch.view_as_real(Gref.t)))
+                print(json.dumps(dict(bloch=bl[0], tx=tx, ty=ty, se=se, march=march, ms=round(ms, 4), speedup=round(ms2 / ms, 3),
+                                      gbs_96=round(96 * M / ms / 1e6), ok=ok)), flush=True)
+            except Exception as ex:
+                print(json.dumps(dict(tx=tx, ty=ty, se=se, march=march, err=str(ex)[:100])), flush=True)
+    c2.set_tuning(0, 0, 0, 0)
