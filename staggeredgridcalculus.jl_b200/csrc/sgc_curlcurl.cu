@@ -27,16 +27,43 @@ template <typename T, typename C, bool ADD>
 int launch_cc_tiles(const CurlCurlParams<T, C> &p, int tx, int ty, int se, dim3 grid, cudaStream_t st) {
 #define CC_CASE(TX, TY, SE, MINB) \
     if (tx == TX && ty == TY && se == SE) return launch_cc_one<T, C, ADD, TX, TY, SE, MINB>(p, grid, st);
-    CC_CASE(32, 8, 4, 2)
     CC_CASE(32, 8, 3, 2)
-    CC_CASE(32, 8, 5, 1)
     CC_CASE(32, 4, 4, 3)
-    CC_CASE(32, 4, 3, 4)
-    CC_CASE(32, 16, 3, 1)
-    CC_CASE(64, 4, 4, 2)
     CC_CASE(64, 4, 3, 2)
 #undef CC_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl: tile %dx%d with %d stages is not built", tx, ty, se);
+}
+
+// version 2 (warp roles): tile 32 x TY, compile-time z-directions
+template <typename T, typename C, bool ADD, int TY, int SE, bool FZ1, bool FZ2>
+int launch_ccw_one(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = ((size_t)SE * 3 * 34 * (TY + 2) + (size_t)3 * 3 * 33 * (TY + 1)) * sizeof(T);
+    auto kern = k_curlcurl3w<T, C, ADD, TY, SE, FZ1, FZ2>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<grid, dim3(32, TY + 1, 1), smem, st>>>(p);
+    return SGC_OK;
+}
+template <typename T, typename C, bool ADD, int TY, int SE>
+int launch_ccw_dirs(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
+    if (p.fwd1[2]) return p.fwd2[2] ? launch_ccw_one<T, C, ADD, TY, SE, true, true>(p, grid, st)
+                                    : launch_ccw_one<T, C, ADD, TY, SE, true, false>(p, grid, st);
+    return p.fwd2[2] ? launch_ccw_one<T, C, ADD, TY, SE, false, true>(p, grid, st)
+                     : launch_ccw_one<T, C, ADD, TY, SE, false, false>(p, grid, st);
+}
+template <typename T, typename C, bool ADD>
+int launch_ccw_tiles(const CurlCurlParams<T, C> &p, int ty, int se, dim3 grid, cudaStream_t st) {
+#define CCW_CASE(TY, SE) if (ty == TY && se == SE) return launch_ccw_dirs<T, C, ADD, TY, SE>(p, grid, st);
+    CCW_CASE(8, 3)
+    CCW_CASE(7, 3)
+    CCW_CASE(7, 4)
+    CCW_CASE(4, 3)
+    CCW_CASE(4, 4)
+#undef CCW_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl: tile 32x%d with %d stages is not built", ty, se);
 }
 
 struct AxisInfo {
@@ -80,15 +107,19 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
     p.c1z_hi = narrow_c<C>(c1->cz_ghost[1]);
     p.Nx = (int)c1->N[0]; p.Ny = (int)c1->N[1]; p.Nz = (int)c1->N[2];
     p.k_begin = (int)k_begin; p.k_end = (int)k_end;
-    // defaults from the 256^3 sweep on B200 (profiles/): 32x8 tile, 4-stage E ring, 2 CTAs/SM
-    const int tx = c2->tile_x ? c2->tile_x : 32;
+    // variant bits 0-3: 0 = warp-role kernel (default), 1 = first generation (two-pass H positions)
+    const int version = c2->variant & 0xF;
+    const int tx = (version == 1 && c2->tile_x) ? c2->tile_x : 32;
     const int ty = c2->tile_y ? c2->tile_y : 8;
-    const int se = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 4;
+    const int se = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 3;
     p.march = c2->march > 0 ? c2->march : 32;
     const int64_t nk = k_end - k_begin;
     dim3 grid((unsigned)((p.Nx + tx - 1) / tx), (unsigned)((p.Ny + ty - 1) / ty), (unsigned)((nk + p.march - 1) / p.march));
     if (grid.y > 65535 || grid.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
-    int s = add_mode ? launch_cc_tiles<T, C, true>(p, tx, ty, se, grid, st) : launch_cc_tiles<T, C, false>(p, tx, ty, se, grid, st);
+    if ((int64_t)p.Nx * p.Ny >= (int64_t)0x7fffffff) return sgc_fail(SGC_ERR_INVALID, "plane too large for the fused curl-of-curl");
+    int s;
+    if (version == 1) s = add_mode ? launch_cc_tiles<T, C, true>(p, tx, ty, se, grid, st) : launch_cc_tiles<T, C, false>(p, tx, ty, se, grid, st);
+    else s = add_mode ? launch_ccw_tiles<T, C, true>(p, ty, se, grid, st) : launch_ccw_tiles<T, C, false>(p, ty, se, grid, st);
     if (s) return s;
     return sgc_check_launch("k_curlcurl3");
 }

@@ -339,4 +339,268 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curlcurl3(const __grid_constan
     cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Version 2: warp roles.  Block = 32 × (TY+1) threads.
+//   every warp w   : B   — H-tile row w, columns 0..31                     (one position per lane)
+//   warps w < TY   : D   — output row w of the plane two steps behind      (one cell per lane)
+//   warp  w = TY   : B′  — the extra H column 32 of rows 0..TY             (lanes 0..TY)
+// so every warp carries two units of work per z-step and the single barrier per step is balanced.
+// The z-directions of C₁ and C₂ are compile-time (FZ1, FZ2); x/y directions only change shared-
+// memory offsets and the sign folded into the coefficients.
+//   phase m:  issue E slot m−1+SE | B(m), B′(m) | D(m−2) | cp.async.wait, __syncthreads
+// ---------------------------------------------------------------------------------------------
+template <typename C>
+struct PosConst {
+    C cxs, cys;  // ±c (direction folded in)
+    int flags;   // bits 0-1 xk, 2-3 yk, 4 xl0, 5 yl0
+};
+template <typename C>
+SGC_D PosConst<C> pos_const(const int *fwd, const int *bc_lo, const int *bc_hi, const C *const *c, int gi, int gj, int Nx, int Ny) {
+    const XYEdge<C> b = xy_edge<C>(fwd, bc_lo, bc_hi, c, gi, gj, Nx, Ny);
+    PosConst<C> r;
+    r.cxs = b.cxs; r.cys = b.cys;
+    r.flags = b.xk | (b.yk << 2) | (b.xl0 ? 16 : 0) | (b.yl0 ? 32 : 0);
+    return r;
+}
+
+// the six ∂ terms with every boundary rule; kept out of line so that the registers of the
+// straight-line path are not sized by this (rarely executed) code
+template <typename T>
+struct SixTerms { T d[6]; };
+template <typename T, typename C, bool FZ>
+__device__ __noinline__ SixTerms<T> curl_point_general(PosConst<C> b, bool fx, bool fy, C cz, int zk, bool zl0, const cplx *e,
+                                                        const int *e_real, T xlo, T xhi, T ylo, T yhi, T zc, T x_yn, T z_yn, T y_xn,
+                                                        T z_xn) {
+    const T xc = FZ ? xlo : xhi, yc = FZ ? ylo : yhi;
+    const C cy = fy ? b.cys : neg(b.cys), cx = fx ? b.cxs : neg(b.cxs);
+    const int xk = b.flags & 3, yk = (b.flags >> 2) & 3;
+    const bool xl0 = (b.flags & 16) != 0, yl0 = (b.flags & 32) != 0;
+    SixTerms<T> r;
+    r.d[0] = dterm<T, C>(FZ, zk, zl0, cz, xc, FZ ? xhi : xlo, e[2], e_real[2]);
+    r.d[1] = dterm<T, C>(FZ, zk, zl0, cz, yc, FZ ? yhi : ylo, e[2], e_real[2]);
+    r.d[2] = dterm<T, C>(fy, yk, yl0, cy, xc, x_yn, e[1], e_real[1]);
+    r.d[3] = dterm<T, C>(fy, yk, yl0, cy, zc, z_yn, e[1], e_real[1]);
+    r.d[4] = dterm<T, C>(fx, xk, xl0, cx, yc, y_xn, e[0], e_real[0]);
+    r.d[5] = dterm<T, C>(fx, xk, xl0, cx, zc, z_xn, e[0], e_real[0]);
+    return r;
+}
+
+// curl at one point from staged values; FZ = z-direction; `fast`: no boundary rule applies
+template <typename T, typename C, bool FZ>
+SGC_D void curl_point(bool fast, const PosConst<C> &b, bool fx, bool fy, C cz, int zk, bool zl0, const cplx *e, const int *e_real,
+                      T xlo, T xhi, T ylo, T yhi, T zc, T x_yn, T z_yn, T y_xn, T z_xn, T &d0, T &d1, T &d2, T &d3, T &d4, T &d5) {
+    const T xc = FZ ? xlo : xhi, yc = FZ ? ylo : yhi;
+    if (fast) {
+        d0 = mul(cz, sub(xhi, xlo)); d1 = mul(cz, sub(yhi, ylo));          // ∂zFx, ∂zFy
+        d2 = mul(b.cys, sub(x_yn, xc)); d3 = mul(b.cys, sub(z_yn, zc));    // ∂yFx, ∂yFz
+        d4 = mul(b.cxs, sub(y_xn, yc)); d5 = mul(b.cxs, sub(z_xn, zc));    // ∂xFy, ∂xFz
+    } else {
+        const SixTerms<T> r = curl_point_general<T, C, FZ>(b, fx, fy, cz, zk, zl0, e, e_real, xlo, xhi, ylo, yhi, zc, x_yn, z_yn, y_xn, z_xn);
+        d0 = r.d[0]; d1 = r.d[1]; d2 = r.d[2]; d3 = r.d[3]; d4 = r.d[4]; d5 = r.d[5];
+    }
+}
+
+template <typename T, typename C, bool ADD, int TY, int SE, bool FZ1, bool FZ2>
+__global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_constant__ CurlCurlParams<T, C> p) {
+    static_assert(SE >= 3, "need at least 3 stages");
+    constexpr int TX = 32;
+    constexpr int NT = 32 * (TY + 1);
+    constexpr int HX = TX + 1, HY = TY + 1, EX = TX + 2, EY = TY + 2;
+    constexpr int HCOMP = HX * HY, ECOMP = EX * EY;
+    constexpr int ESTAGE = 3 * ECOMP, HSTAGE = 3 * HCOMP;
+    constexpr int NLD = (ECOMP + NT - 1) / NT;
+    static_assert(HY <= 32, "the extra column is handled by one warp");
+    extern __shared__ __align__(16) unsigned char sgc_smem_raw[];
+    T *const sE = reinterpret_cast<T *>(sgc_smem_raw);
+    T *const sH = sE + SE * ESTAGE;
+
+    const int lane = threadIdx.x, w = threadIdx.y;
+    const int tid = w * 32 + lane;
+    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz;
+    const int64_t sy = Nx, sz = (int64_t)Nx * Ny;
+    const bool fx1 = p.fwd1[0], fy1 = p.fwd1[1], fx2 = p.fwd2[0], fy2 = p.fwd2[1];
+    const int s1x = fx1 ? 1 : -1, s1y = fy1 ? 1 : -1, s2x = fx2 ? 1 : -1, s2y = fy2 ? 1 : -1;
+    constexpr int s1z = FZ1 ? 1 : -1, s2z = FZ2 ? 1 : -1;
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int hx0 = i0 + min(0, s2x), hy0 = j0 + min(0, s2y);
+    const int ex0 = hx0 + min(0, s1x), ey0 = hy0 + min(0, s1y);
+    const T Z = zero_of(T{});
+    const bool tile_plain = (hx0 >= 1) && (hx0 + HX - 1 <= Nx - 2) && (hy0 >= 1) && (hy0 + HY - 1 <= Ny - 2);
+    const bool lo_ext = (p.ghost_lo[0] != nullptr), hi_ext = (p.ghost_hi[0] != nullptr);
+    const int ox1 = s1x < 0 ? 1 : 0, oy1 = s1y < 0 ? 1 : 0;
+    const int e_dx = s1x, e_dy = s1y * EX;
+
+    // ---- loader duty ------------------------------------------------------------------------------
+    int ld_g[NLD];  // element offset inside a plane (fits 32 bits: Nx·Ny < 2^31 is checked on the host)
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+        const int q = tid + u * NT;
+        const int py = q / EX, px = q - py * EX;
+        ld_g[u] = (q < ECOMP) ? wrap_index(ey0 + py, Ny) * Nx + wrap_index(ex0 + px, Nx) : -1;
+    }
+    // ---- role B: H position (row w, column lane) -----------------------------------------------------
+    const int qa = (w + oy1) * EX + (lane + ox1);  // E-tile index of the position
+    const int pa = w * HX + lane;                  // H-tile index
+    const PosConst<C> ca = pos_const<C>(p.fwd1, p.bc1_lo, p.bc1_hi, p.c1, wrap_index(hx0 + lane, Nx), wrap_index(hy0 + w, Ny), Nx, Ny);
+    T axlo = Z, aylo = Z;
+    // ---- second role -------------------------------------------------------------------------------------
+    const bool roleD = (w < TY);
+    const bool roleB2 = (w == TY) && (lane < HY);
+    int qb;  // D: H-tile index of the cell;  B′: E-tile index of the position
+    PosConst<C> cb;
+    const int i = i0 + lane, j = j0 + w;
+    const bool valid = roleD && (i < Nx) && (j < Ny);
+    if (roleD) {
+        qb = (w + (s2y < 0 ? 1 : 0)) * HX + (lane + (s2x < 0 ? 1 : 0));
+        cb = pos_const<C>(p.fwd2, p.bc2_lo, p.bc2_hi, p.c2, valid ? i : 0, valid ? j : 0, Nx, Ny);
+    } else {
+        const int py = roleB2 ? lane : 0;
+        qb = (py + oy1) * EX + (TX + ox1);
+        cb = pos_const<C>(p.fwd1, p.bc1_lo, p.bc1_hi, p.c1, wrap_index(hx0 + TX, Nx), wrap_index(hy0 + py, Ny), Nx, Ny);
+    }
+    const int pb = (roleB2 ? lane : 0) * HX + TX;  // H-tile index of the B′ position
+    const int h_dx = s2x, h_dy = s2y * HX;
+    T bxlo = Z, bylo = Z;
+
+    const int k0 = p.k_begin + blockIdx.z * p.march;
+    const int k1 = min(k0 + p.march, p.k_end);
+    if (k0 >= k1) return;
+    const int n = k1 - k0;
+    const int hb = k0 + min(0, s2z);
+    const int eb = hb + min(0, s1z);
+
+    // ---- producer ------------------------------------------------------------------------------------------
+    int jj_issue = 0, stage_issue = 0;
+    auto issue = [&]() {
+        if (jj_issue <= n + 1) {
+            const int ke = eb + jj_issue;
+            const T *s0, *s1, *s2;
+            if (ke >= 0 && ke < Nz) {
+                const int64_t off = (int64_t)ke * sz;
+                s0 = p.F[0] + off; s1 = p.F[1] + off; s2 = p.F[2] + off;
+            } else if (ke < 0 && lo_ext) { s0 = p.ghost_lo[0]; s1 = p.ghost_lo[1]; s2 = p.ghost_lo[2]; }
+            else if (ke >= Nz && hi_ext) { s0 = p.ghost_hi[0]; s1 = p.ghost_hi[1]; s2 = p.ghost_hi[2]; }
+            else {
+                const int64_t off = (int64_t)wrap_index(ke, Nz) * sz;
+                s0 = p.F[0] + off; s1 = p.F[1] + off; s2 = p.F[2] + off;
+            }
+            const bool centre = FZ1 ? (jj_issue <= n) : (jj_issue >= 1);
+            T *st = sE + stage_issue * ESTAGE + tid;
+#pragma unroll
+            for (int u = 0; u < NLD; ++u) {
+                if (ld_g[u] >= 0) {
+                    cp_async_elem(st + u * NT, s0 + ld_g[u]);
+                    cp_async_elem(st + ECOMP + u * NT, s1 + ld_g[u]);
+                    if (centre) cp_async_elem(st + 2 * ECOMP + u * NT, s2 + ld_g[u]);
+                }
+            }
+        }
+        cp_async_commit();
+        ++jj_issue;
+        stage_issue = (stage_issue + 1 == SE) ? 0 : stage_issue + 1;
+    };
+#pragma unroll
+    for (int q = 0; q < SE; ++q) issue();
+    cp_async_wait<SE - 2>();
+    __syncthreads();
+
+    int est_lo = 0;  // ring stage of E slot m
+    int hst = 0;     // H stage of slot m  (m % 3)
+    int64_t off_out = (int64_t)k0 * sz + (int64_t)j * sy + i;
+
+    // one H value from the staged E planes (role B and role B′ share this)
+    auto h_point = [&](int m, int q, const PosConst<C> &c, T &xlo_c, T &ylo_c, int pos, bool fast, C cz, int zk, bool zl0) {
+        const int est_hi = (est_lo + 1 == SE) ? 0 : est_lo + 1;
+        const T *slo = sE + est_lo * ESTAGE;
+        const T *shi = sE + est_hi * ESTAGE;
+        const T *sc = FZ1 ? slo : shi;
+        if (m == 0) { xlo_c = slo[q]; ylo_c = slo[ECOMP + q]; }
+        const T xhi = shi[q], yhi = shi[ECOMP + q];
+        const T zc = sc[2 * ECOMP + q];
+        const T x_yn = sc[q + e_dy], z_yn = sc[2 * ECOMP + q + e_dy];
+        const T y_xn = sc[ECOMP + q + e_dx], z_xn = sc[2 * ECOMP + q + e_dx];
+        T d0, d1, d2, d3, d4, d5;
+        curl_point<T, C, FZ1>(fast, c, fx1, fy1, cz, zk, zl0, p.e1, p.e1_real, xlo_c, xhi, ylo_c, yhi, zc, x_yn, z_yn, y_xn, z_xn,
+                              d0, d1, d2, d3, d4, d5);
+        T *hout = sH + hst * HSTAGE + pos;
+        hout[0] = add(add(Z, neg(d1)), d3);  // Gv .= 0 ; += (−∂zFy) ; += ∂yFz   (curl.jl:66-91)
+        hout[HCOMP] = add(d0, neg(d5));
+        hout[2 * HCOMP] = add(neg(d2), d4);
+        xlo_c = xhi;
+        ylo_c = yhi;
+    };
+
+    int hk = hb;  // grid plane of H slot m (un-wrapped)
+    for (int m = 0; m <= n + 1; ++m, ++hk) {
+        if (m >= 1) issue();  // E slot m − 1 + SE → the stage slot m − 1 used (free since the last barrier)
+        if (m <= n) {
+            // ================= B(m), B′(m): H plane hb + m =============================================
+            const bool ghostH = (hk < 0 && lo_ext) || (hk >= Nz && hi_ext);
+            const int kk = ghostH ? hk : ((hk >= 0 && hk < Nz) ? hk : wrap_index(hk, Nz));
+            const C cz = ghostH ? (hk < 0 ? p.c1z_lo : p.c1z_hi) : p.c1[2][kk];
+            int zk = 0;
+            bool zl0 = false, ghost_plain = false;
+            if (ghostH) {
+                const int side = (hk < 0) ? p.bc1_lo[2] : p.bc1_hi[2];
+                if (side == BC_BLOCH) zk = 1;
+                else ghost_plain = true;
+            } else if (FZ1) {
+                if (kk == Nz - 1) zk = (p.bc1_hi[2] == BC_BLOCH) ? 1 : (p.bc1_hi[2] == BC_SYM ? 2 : 0);
+                zl0 = (kk == 0) && (p.bc1_lo[2] == BC_SYM);
+            } else if (kk == 0) {
+                zk = (p.bc1_lo[2] == BC_BLOCH) ? 1 : (p.bc1_lo[2] == BC_SYM ? 2 : 0);
+            }
+            const bool fast = tile_plain && (ghostH ? ghost_plain : (kk > 0 && kk < Nz - 1));
+            h_point(m, qa, ca, axlo, aylo, pa, fast, cz, zk, zl0);
+            if (roleB2) h_point(m, qb, cb, bxlo, bylo, pb, fast, cz, zk, zl0);
+        }
+        if (roleD && m >= 2) {
+            // ================= D(m − 2): output plane k0 + m − 2 from H slots m − 2 (lo), m − 1 (hi) =======
+            const int k = k0 + m - 2;
+            T g0 = Z, g1 = Z, g2 = Z;
+            if (ADD && valid) { g0 = ldg_plain(p.G[0] + off_out); g1 = ldg_plain(p.G[1] + off_out); g2 = ldg_plain(p.G[2] + off_out); }
+            const int st_hi = (hst == 0) ? 2 : hst - 1;     // slot m − 1
+            const int st_lo = (st_hi == 0) ? 2 : st_hi - 1;  // slot m − 2
+            const T *hlo = sH + st_lo * HSTAGE;
+            const T *hhi = sH + st_hi * HSTAGE;
+            const T *hc = FZ2 ? hlo : hhi;
+            if (m == 2) { bxlo = hlo[qb]; bylo = hlo[HCOMP + qb]; }
+            const T xhi = hhi[qb], yhi = hhi[HCOMP + qb];
+            const T zc = hc[2 * HCOMP + qb];
+            const T x_yn = hc[qb + h_dy], z_yn = hc[2 * HCOMP + qb + h_dy];
+            const T y_xn = hc[HCOMP + qb + h_dx], z_xn = hc[2 * HCOMP + qb + h_dx];
+            const C cz = p.c2[2][k];
+            int zk = 0;
+            bool zl0 = false;
+            if (FZ2) {
+                if (k == Nz - 1) zk = (p.bc2_hi[2] == BC_BLOCH) ? 1 : (p.bc2_hi[2] == BC_SYM ? 2 : 0);
+                zl0 = (k == 0) && (p.bc2_lo[2] == BC_SYM);
+            } else if (k == 0) {
+                zk = (p.bc2_lo[2] == BC_BLOCH) ? 1 : (p.bc2_lo[2] == BC_SYM ? 2 : 0);
+            }
+            T d0, d1, d2, d3, d4, d5;
+            curl_point<T, C, FZ2>(tile_plain && k > 0 && k < Nz - 1, cb, fx2, fy2, cz, zk, zl0, p.e2, p.e2_real, bxlo, xhi, bylo, yhi, zc,
+                                  x_yn, z_yn, y_xn, z_xn, d0, d1, d2, d3, d4, d5);
+            T gx, gy, gz;
+            if (ADD) { gx = add(add(g0, neg(d1)), d3); gy = add(add(g1, d0), neg(d5)); gz = add(add(g2, neg(d2)), d4); }
+            else     { gx = add(add(Z, neg(d1)), d3);  gy = add(d0, neg(d5));          gz = add(neg(d2), d4); }
+            if (valid) {
+                stg_stream(p.G[0] + off_out, gx);
+                stg_stream(p.G[1] + off_out, gy);
+                stg_stream(p.G[2] + off_out, gz);
+            }
+            bxlo = xhi;
+            bylo = yhi;
+            off_out += sz;
+        }
+        if (m <= n) {
+            est_lo = (est_lo + 1 == SE) ? 0 : est_lo + 1;
+            hst = (hst == 2) ? 0 : hst + 1;
+        }
+        cp_async_wait<SE - 3>();  // E slot m + 2 has landed (for this thread) …
+        __syncthreads();          // … and for everybody; H plane m is complete; E slot m is free
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace sgc

@@ -426,7 +426,9 @@ def test_fused_divg_grad_slab_split_equals_whole(S):
 # ------------------------------------------------------------------------------------------------
 # fused curl-of-curl (k_curlcurl3): one pass, H never written — bit-identical to two apply_curl!
 # ------------------------------------------------------------------------------------------------
-CURLCURL_TILINGS = [(0, 0, 0, 0), (32, 8, 3, 3), (32, 8, 5, 5), (32, 4, 2, 4), (32, 4, 7, 3), (32, 16, 4, 3), (64, 4, 1, 4), (64, 4, 6, 3)]
+# (tile_x, tile_y, march, E-ring stages, kernel version: 0 = warp roles, 1 = first generation)
+CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 8, 3, 3, 0), (32, 7, 5, 4, 0), (32, 4, 2, 4, 0), (32, 7, 1, 3, 0), (32, 4, 7, 3, 0),
+                    (32, 8, 3, 3, 1), (32, 4, 2, 4, 1), (64, 4, 6, 3, 1)]
 
 
 def _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, tilings, what):
@@ -446,13 +448,13 @@ def _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, ti
         c1.apply(H, Fd, "=")
         c2.apply(Gref, H, op)
         ref = Gref.numpy()
-        for (tx, ty, march, se) in tilings:
-            c2.set_tuning(tx, ty, march, se << 4)
+        for (tx, ty, march, se, ver) in tilings:
+            c2.set_tuning(tx, ty, march, (se << 4) | ver)
             Gd = dev(S, G0)
             n0 = S.launch_count()
             c2.apply_after(c1, Gd, Fd, op)
             assert S.launch_count() == n0 + 1
-            assert_parity(Gd.numpy(), ref, f"{what} {op} tile=({tx},{ty}) march={march} stages={se}", exact=True)
+            assert_parity(Gd.numpy(), ref, f"{what} {op} tile=({tx},{ty}) march={march} stages={se} v{ver}", exact=True)
         c2.set_tuning(0, 0, 0, 0)
     # and against the oracle (two apply_curl! of the restatement)
     Href = np.zeros_like(F)
@@ -475,7 +477,7 @@ def test_fused_curlcurl_equals_two_curls(S, N, cplx_field, cplx_coef):
         for isbloch in ([True] * 3, [False] * 3, [True, False, True], [False, True, False]):
             if not all(isbloch[d] or N[d] >= 2 or not (isfwd1[d] or isfwd2[d]) for d in range(3)):
                 continue  # forward + symmetric on an axis of length 1 is rejected (reads Fu[2])
-            _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, CURLCURL_TILINGS[:3],
+            _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, CURLCURL_TILINGS[:3] + CURLCURL_TILINGS[6:7],
                            f"curlcurl N={N} fwd1={isfwd1} fwd2={isfwd2} bloch={isbloch}")
 
 

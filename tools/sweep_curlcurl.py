@@ -30,13 +30,13 @@ for bl in ([False] * 3, [True] * 3):
         c1.apply(H, E, "="); c2.apply(Gref, H, "=")
     ms2 = timeit(two)
     print(json.dumps(dict(bloch=bl[0], mode="two fused curls", ms=round(ms2, 4), gcell_pairs=round(M / ms2 / 1e6, 2), gbs_192=round(192 * M / ms2 / 1e6))), flush=True)
-    for tx, ty, se in ((32, 8, 4), (32, 8, 3), (32, 8, 5), (32, 4, 4), (32, 4, 3), (32, 16, 3), (64, 4, 4), (64, 4, 3)):
+    for tx, ty, se, ver in ((32, 8, 3, 0), (32, 7, 3, 0), (32, 7, 4, 0), (32, 4, 3, 0), (32, 4, 4, 0), (32, 8, 3, 1)):
         for march in (16, 32, 64):
-            c2.set_tuning(tx, ty, march, se << 4)
+            c2.set_tuning(tx, ty, march, (se << 4) | ver)
             try:
                 ms = timeit(lambda: c2.apply_after(c1, G, E, "="))
                 ok = bool(torch.equal(torch.view_as_real(G.t), torch.view_as_real(Gref.t)))
-                print(json.dumps(dict(bloch=bl[0], tx=tx, ty=ty, se=se, march=march, ms=round(ms, 4), speedup=round(ms2 / ms, 3),
+                print(json.dumps(dict(bloch=bl[0], ver=ver, tx=tx, ty=ty, se=se, march=march, ms=round(ms, 4), speedup=round(ms2 / ms, 3),
                                       gbs_96=round(96 * M / ms / 1e6), ok=ok)), flush=True)
             except Exception as ex:
                 print(json.dumps(dict(tx=tx, ty=ty, se=se, march=march, err=str(ex)[:100])), flush=True)
