@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="side experiments only: skip the host-array leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] (2-D operators) and fused curl-of-curl side measurements")
+    ap.add_argument("--serial-e2e", action="store_true", help="N > 1: H2D, step, D2H without the chunked pipeline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     global NLOCAL
@@ -204,6 +206,8 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU: the product path has no CPU fallback"
     torch.cuda.set_device(local_rank)
+    from sgc_b200.hostpipe import bind_to_gpu_numa_node
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers on the GPU's own node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -331,6 +335,18 @@ def main():
                 raise RuntimeError("pipelined host path disagrees with the serial host path")
             e2e_step = lambda: pipe.run(E_host, Out_host)
             e2e_mode = "z-chunked (16) full-duplex pipeline: H2D | 2 fused curls per chunk | D2H on three streams"
+        elif arena is not None and not args.serial_e2e:  # the same pipeline per rank; interface planes after a peer barrier
+            from sgc_b200.hostpipe import HostSlabCurlCurl
+            pipe = HostSlabCurlCurl(c_dual, c_prim, E, H, E2, nchunks=16)
+            e2e_step_serial()
+            ref_out = Out_host.clone()
+            Out_host.zero_()
+            pipe.run(E_host, Out_host)
+            if not torch.equal(ref_out, Out_host):
+                raise RuntimeError("pipelined slab host path disagrees with the serial host path")
+            e2e_step = lambda: pipe.run(E_host, Out_host)
+            e2e_mode = ("per-rank z-chunked (16) full-duplex pipeline, interface planes after a peer barrier; "
+                        f"process bound to the GPU's NUMA node ({'yes' if numa_cpus else 'topology not exposed'})")
 
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
@@ -387,6 +403,10 @@ def main():
 
     if world == 1 and not args.no_assembly:
         out["assembly"] = bench_assembly(S, torch, peak)
+        out["assembly_c128"] = bench_assembly(S, torch, peak, cplx=True)
+    if world == 1 and not args.no_extras:
+        E_host = Out_host = None  # release the pinned staging arrays
+        out["other_configs"] = bench_other_configs(S, torch, peak, c_dual.backend.op, c_prim.backend.op, E, E2, ms_step)
     if world == 1 and not args.no_cpu_baseline:
         rate, threads, sample = cpu_reference_rate(dprim, ddual, NLOCAL[2], args.cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
@@ -396,7 +416,7 @@ def main():
         dist.destroy_process_group()
 
 
-def bench_assembly(S, torch, peak):
+def bench_assembly(S, torch, peak, cplx=False):
     """Second half of the metric: create_curl CSC assembly in nnz/s (BASELINE.json configs[3]:
     512³, Float64, uniform, all-Bloch, nnz = 12·512³ = 1 610 612 736), through the C ABI with
     caller-owned output arrays (what the Julia shim does): count pass + scan + nnz read-back, then
@@ -410,14 +430,15 @@ def bench_assembly(S, torch, peak):
     res = {}
     try:
         h = C.c_void_p()
+        e = list(np.exp(-2j * np.pi * np.array([0.1, 0.2, 0.3]))) if cplx else [1.0] * 3
         check(lib.sgc_asm_create_curl(C.byref(h), 3, int64s(N), ints([1, 1, 1]), None, 0, ints([1, 1, 1]),
-                                      scalars2([1.0] * 3), 0, ints([1, 2, 3]), 3, ints([1, 2, 3]), 3, ints([1, 2, 3]), 1))
+                                      scalars2(e), int(cplx), ints([1, 2, 3]), 3, ints([1, 2, 3]), 3, ints([1, 2, 3]), 1))
         st = stream_handle()
         nnz = C.c_int64()
         check(lib.sgc_asm_count(h, C.byref(nnz), st))
         colptr = torch.empty(3 * M + 1, dtype=torch.int64, device="cuda")
         rowval = torch.empty(nnz.value, dtype=torch.int64, device="cuda")
-        nzval = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+        nzval = torch.empty(nnz.value, dtype=torch.complex128 if cplx else torch.float64, device="cuda")
 
         def once():
             check(lib.sgc_asm_set_row_range(h, 0, 3 * M))  # drops the cached count: time the whole assembly
@@ -437,13 +458,78 @@ def bench_assembly(S, torch, peak):
         ms = ev0.elapsed_time(ev1) / reps
         ok = bool((colptr[1:] - colptr[:-1] == 4).all()) and int(colptr[-1]) == nnz.value + 1
         lib.sgc_asm_destroy(h)
-        alg = nnz.value * 16 + (3 * M + 1) * 8
-        res = {"workload": "create_curl 512^3 Float64 uniform all-Bloch, order_cmpfirst=true; colptr+rowval+nzval on device (29.0 GB)",
+        alg = nnz.value * (24 if cplx else 16) + (3 * M + 1) * 8
+        res = {"workload": f"create_curl 512^3 {'ComplexF64 (Bloch phases)' if cplx else 'Float64'} uniform all-Bloch, order_cmpfirst=true; "
+                           f"colptr+rowval+nzval on device ({alg / 1e9:.1f} GB)",
                "nnz": nnz.value, "ms": ms, "nnz_per_s": nnz.value / (ms * 1e-3), "algorithmic_bytes": alg,
                "achieved_gbs": alg / (ms * 1e-3) / 1e9, "frac": alg / (ms * 1e-3) / 1e9 / peak, "structure_ok": ok,
-               "includes": "count pass + scan + nnz read-back (host sync) + single fill pass"}
+               "includes": "nnz and per-CTA offsets in closed form (no count pass, no scan) + single fill pass writing colptr, rowval, nzval"}
+        del colptr, rowval, nzval
+        torch.cuda.empty_cache()
     except Exception as ex:  # out of memory on a shared box etc.
         res = {"error": str(ex)[:200]}
+    return res
+
+
+def _time(torch, fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def bench_other_configs(S, torch, peak, c_dual, c_prim, E, E2, ms_two_curls):
+    """Side measurements (not the headline): the fused curl-of-curl on the headline grid, the 3-D
+    divergence / gradient, and BASELINE.json configs[2] — 2-D 8192² Float64 ∂ / m̂ / TE / TM operators
+    with PEC/PMC (symmetric) boundaries.  GB/s are ALGORITHMIC bytes / time."""
+    res = {}
+    try:
+        M = NLOCAL[0] * NLOCAL[1] * NLOCAL[2]
+        ms = _time(torch, lambda: c_prim.apply_after(c_dual, E2, E, "="))
+        res["curlcurl_fused"] = {"what": "E' = C_prim(C_dual E) in ONE kernel, H kept in shared memory (bit-identical to the two launches)",
+                                 "ms": ms, "ms_two_launches": ms_two_curls, "gcell_updates_per_s": 2 * M / ms / 1e6,
+                                 "gbs_of_96B_per_cell": 96 * M / ms / 1e6, "frac": 96 * M / ms / 1e6 / peak}
+        N3 = NLOCAL
+        rng = np.random.default_rng(3)
+        d3 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for n in N3]
+        g = S.DeviceArray.zeros(N3)
+        dv = S.Operator.divg(S.SGC_C128, N3, [True] * 3, d3, [False] * 3, [1.0] * 3)
+        gr = S.Operator.grad(S.SGC_C128, N3, [False] * 3, d3, [False] * 3, [1.0] * 3)
+        for name, fn in (("divg_3d_c128", lambda: dv.apply(g, E, "=")), ("grad_3d_c128", lambda: gr.apply(E2, g, "="))):
+            ms = _time(torch, fn)
+            res[name] = {"ms": ms, "launches": 1, "gbs": 64 * M / ms / 1e6, "frac": 64 * M / ms / 1e6 / peak}
+        del g
+        n = 8192
+        N2, M2 = (n, n), n * n
+        d = rng.uniform(0.5, 1.5, n)
+        F = S.DeviceArray(torch.rand(M2, device="cuda", dtype=torch.float64), N2)
+        G = S.DeviceArray.zeros(N2, np.float64)
+        F2 = S.DeviceArray(torch.rand(2 * M2, device="cuda", dtype=torch.float64), N2 + (2,))
+        G1 = S.DeviceArray.zeros(N2 + (1,), np.float64)
+        ops = []
+        for nw in (1, 2):
+            ops.append((f"partial_nw{nw}_fwd_set", S.Operator.partial(S.SGC_F64, N2, nw, True, d, False), G, F, "=", 16))
+            ops.append((f"partial_nw{nw}_bwd_add", S.Operator.partial(S.SGC_F64, N2, nw, False, d, False), G, F, "+=", 24))
+            ops.append((f"mhat_arith_nw{nw}", S.Operator.mhat(S.SGC_F64, N2, nw, True, None, None, False), G, F, "=", 16))
+            ops.append((f"mhat_weighted_nw{nw}", S.Operator.mhat(S.SGC_F64, N2, nw, False, d, d, False), G, F, "=", 16))
+        ops.append(("TE_curl_1x2", S.Operator.curl(S.SGC_F64, N2, [True, True], [d, d], [False, False], [1.0, 1.0], cmp_shp=[1, 2],
+                                                   cmp_out=[3], cmp_in=[1, 2]), G1, F2, "=", 24))
+        ops.append(("TM_curl_2x1", S.Operator.curl(S.SGC_F64, N2, [False, False], [d, d], [False, False], [1.0, 1.0], cmp_shp=[1, 2],
+                                                   cmp_out=[1, 2], cmp_in=[3]), F2, G1, "=", 24))
+        two_d = {}
+        for name, o, Gd, Fd, mode, B in ops:
+            ms = _time(torch, lambda: o.apply(Gd, Fd, mode))
+            two_d[name] = {"ms": ms, "gcell_per_s": M2 / ms / 1e6, "gbs": B * M2 / ms / 1e6, "frac": B * M2 / ms / 1e6 / peak,
+                           "launches": o.launches(mode)}
+        res["ops_2d_8192_f64_pec_pmc"] = two_d
+    except Exception as ex:
+        res["error"] = str(ex)[:200]
     return res
 
 

@@ -110,7 +110,7 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
     // variant bits 0-3: 0 = warp-role kernel (default), 1 = first generation (two-pass H positions)
     const int version = c2->variant & 0xF;
     const int tx = (version == 1 && c2->tile_x) ? c2->tile_x : 32;
-    const int ty = c2->tile_y ? c2->tile_y : 8;
+    const int ty = c2->tile_y ? c2->tile_y : (version == 1 ? 8 : 7);  // 32x7 outputs + 1 halo row = 8 warps, 2 CTAs/SM at 128 registers
     const int se = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 3;
     p.march = c2->march > 0 ? c2->march : 32;
     const int64_t nk = k_end - k_begin;

@@ -1,5 +1,6 @@
 // sgc_fused.cuh — one-launch kernels for the small operator compositions (sm_100a).
 //
+//   apply_∂!     (matrixfree/differential/partial.jl:33-385, 2-D and 3-D arrays)   Gv OP ∂w Fu
 //   apply_divg!  (matrixfree/differential/divergence.jl:41-66)   g   OP Σ_w ∂w F_w
 //   apply_grad!  (matrixfree/differential/gradient.jl:41-59)     G_w OP ∂w f
 //   2-D sub-curls of apply_curl! (matrixfree/differential/curl.jl:52-137 with cmp_shp of length 2):
@@ -31,7 +32,8 @@ struct PatDesc {
     int nt, nin, nout;
     int out[3], in[3], axis[3];
 };
-enum : int { PAT_GATHER_XY = 0, PAT_GATHER_YX = 1, PAT_GATHER_XYZ = 2, PAT_SCATTER_XY = 3, PAT_SCATTER_YX = 4, PAT_SCATTER_XYZ = 5, PAT_COUNT = 6 };
+enum : int { PAT_GATHER_XY = 0, PAT_GATHER_YX = 1, PAT_GATHER_XYZ = 2, PAT_SCATTER_XY = 3, PAT_SCATTER_YX = 4, PAT_SCATTER_XYZ = 5,
+              PAT_ONE_X = 6, PAT_ONE_Y = 7, PAT_ONE_Z = 8, PAT_COUNT = 9 };
 template <int P> struct Pat;
 template <> struct Pat<PAT_GATHER_XY>   { static constexpr PatDesc D{2, 2, 1, {0, 0, 0}, {0, 1, 0}, {0, 1, 0}}; };  // divg 2-D
 template <> struct Pat<PAT_GATHER_YX>   { static constexpr PatDesc D{2, 2, 1, {0, 0, 0}, {0, 1, 0}, {1, 0, 0}}; };  // TE sub-curl
@@ -39,6 +41,9 @@ template <> struct Pat<PAT_GATHER_XYZ>  { static constexpr PatDesc D{3, 3, 1, {0
 template <> struct Pat<PAT_SCATTER_XY>  { static constexpr PatDesc D{2, 1, 2, {0, 1, 0}, {0, 0, 0}, {0, 1, 0}}; };  // grad 2-D
 template <> struct Pat<PAT_SCATTER_YX>  { static constexpr PatDesc D{2, 1, 2, {0, 1, 0}, {0, 0, 0}, {1, 0, 0}}; };  // TM sub-curl
 template <> struct Pat<PAT_SCATTER_XYZ> { static constexpr PatDesc D{3, 1, 3, {0, 1, 2}, {0, 0, 0}, {0, 1, 2}}; };  // grad 3-D
+template <> struct Pat<PAT_ONE_X>       { static constexpr PatDesc D{1, 1, 1, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}}; };  // apply_∂! along x
+template <> struct Pat<PAT_ONE_Y>       { static constexpr PatDesc D{1, 1, 1, {0, 0, 0}, {0, 0, 0}, {1, 0, 0}}; };  // apply_∂! along y
+template <> struct Pat<PAT_ONE_Z>       { static constexpr PatDesc D{1, 1, 1, {0, 0, 0}, {0, 0, 0}, {2, 0, 0}}; };  // apply_∂! along z
 
 template <typename C>
 struct FTerm {

@@ -21,7 +21,7 @@ from ._lib import lib, check
 from .device import DeviceArray
 from .matrixfree import Operator
 
-__all__ = ["HostCurlCurl"]
+__all__ = ["HostCurlCurl", "HostSlabCurlCurl", "bind_to_gpu_numa_node"]
 
 
 class HostCurlCurl:
@@ -74,4 +74,111 @@ class HostCurlCurl:
                 done.record(self.s_cmp)
                 self.s_out.wait_event(done)
                 self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, kb, ke, self.s_out)
+        self.s_out.synchronize()
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned host
+    buffers allocated afterwards are first-touched on that node and the PCIe copies do not cross the
+    socket interconnect.  One process per GPU (torchrun) otherwise lands on arbitrary cores.
+    Returns the CPU list it bound to, or None when the topology is not exposed."""
+    import os
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
+
+
+class HostSlabCurlCurl:
+    """The same z-chunked duplex pipeline for one rank of a z-slab-decomposed grid (N > 1 GPUs, fields in
+    a `PeerArena`).  Planes whose stencil stays inside the slab stream through exactly as on one GPU;
+    the two planes that need a neighbour's data are finished at the end, after a device-side barrier
+    (the neighbour's E has arrived / its H is complete), and copied out last:
+
+        forward C₁ : H[Nz−1] needs E[0] of rank+1          (hi interface)
+        backward C₂: E′[0]   needs H[Nz−1] of rank−1       (lo interface)
+    """
+
+    def __init__(self, slab_fwd, slab_bwd, E: DeviceArray, H: DeviceArray, E2: DeviceArray, nchunks=16):
+        self.s1, self.s2 = slab_fwd, slab_bwd
+        assert slab_fwd.arena is not None and slab_fwd.plan["boundary"] == "top" and slab_bwd.plan["boundary"] == "bottom"
+        self.N = slab_fwd.N
+        self.plane = self.N[0] * self.N[1]
+        self.M = self.plane * self.N[2]
+        nz = self.N[2]
+        nchunks = max(1, min(nchunks, nz))
+        cuts = [(nz * c) // nchunks for c in range(nchunks + 1)]
+        self.chunks = list(zip(cuts[:-1], cuts[1:]))
+        self.s_in, self.s_cmp, self.s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        self.E, self.H, self.E2 = E, H, E2
+
+    _copy_planes = HostCurlCurl._copy_planes
+
+    def _ghost(self, slab, F):
+        plan, Nz = slab.plan, self.N[2]
+        if plan["recv_from"] is None:
+            return None
+        base = slab.arena.peer_ptr(F, plan["recv_from"])
+        kpl = 0 if plan["boundary"] == "top" else Nz - 1
+        return [base + (c * self.M + kpl * self.plane) * 16 for c in range(2)] + [None]
+
+    def run(self, E_host: torch.Tensor, Out_host: torch.Tensor):
+        nz = self.N[2]
+        hi_iface = self.s1.plan["recv_from"] is not None   # my top H plane needs the upper neighbour's E
+        lo_iface = self.s2.plan["recv_from"] is not None   # my bottom E′ plane needs the lower neighbour's H
+        c1, c2 = self.s1.backend.op, self.s2.backend.op
+        last = len(self.chunks) - 1
+        start = torch.cuda.Event()
+        start.record(torch.cuda.current_stream())
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            s.wait_event(start)
+        for c, (a, b) in enumerate(self.chunks):
+            self._copy_planes(lib.sgc_memcpy_h2d, self.E, E_host, a, b, self.s_in)
+            arrived = torch.cuda.Event()
+            arrived.record(self.s_in)
+            self.s_cmp.wait_event(arrived)
+            kb = a - 1 if c > 0 else 0
+            ke = (nz - 1 if hi_iface else nz) if c == last else b - 1
+            if ke > kb:
+                c1.apply_range(self.H, self.E, "=", kb, ke, None, stream=self.s_cmp)
+                kb2 = max(kb, 1) if lo_iface else kb
+                if ke > kb2:
+                    c2.apply_range(self.E2, self.H, "=", kb2, ke, None, stream=self.s_cmp)
+                    done = torch.cuda.Event()
+                    done.record(self.s_cmp)
+                    self.s_out.wait_event(done)
+                    self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, kb2, ke, self.s_out)
+        # the interface planes: every rank's E has landed → H top plane; every rank's H is complete → E′
+        with torch.cuda.stream(self.s_cmp):
+            self.s1.arena.barrier()
+            if hi_iface:
+                c1.apply_range(self.H, self.E, "=", nz - 1, nz, self._ghost(self.s1, self.E), stream=self.s_cmp)
+            self.s1.arena.barrier()
+            if lo_iface:
+                c2.apply_range(self.E2, self.H, "=", 0, 1, self._ghost(self.s2, self.H), stream=self.s_cmp)
+            if hi_iface:
+                c2.apply_range(self.E2, self.H, "=", nz - 1, nz, None, stream=self.s_cmp)
+            self.s1.arena.barrier()  # nobody overwrites E / H of the next pass while a neighbour still reads them
+        done = torch.cuda.Event()
+        done.record(self.s_cmp)
+        self.s_out.wait_event(done)
+        if lo_iface:
+            self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, 0, 1, self.s_out)
+        if hi_iface:
+            self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, nz - 1, nz, self.s_out)
         self.s_out.synchronize()
