@@ -161,6 +161,34 @@ function apply_curl!(G::DeviceArray{T,K₊₁}, F::DeviceArray{T,K₊₁}, ::Val
     return nothing
 end
 
+# apply_curlcurl!  — G OP ∇₂×(∇₁×F): the pair of apply_curl! calls either side of the intermediate field
+# (src/matrixfree/differential/curl.jl:52-137 twice; matrix form `Cv*Cu`, test/curl.jl:123-153) in ONE pass over
+# memory; bit-identical to the two calls.  New entry point (the reference has no fused form).
+function apply_curlcurl!(G::DeviceArray{T,4}, F::DeviceArray{T,4}, ::Val{OP}, isfwd₁, ∆l₁⁻¹::NTuple{3,AbstractVector{<:Number}},
+                         isfwd₂, ∆l₂⁻¹::NTuple{3,AbstractVector{<:Number}}, isbloch, e⁻ⁱᵏᴸ; α₁::Number=1.0, α₂::Number=1.0) where {T,OP}
+    N = Int64[size(G)[1:3]...]
+    ops = Ptr{Cvoid}[C_NULL, C_NULL]
+    for (q, (isfwd, ∆l⁻¹, α)) in enumerate(((isfwd₁, ∆l₁⁻¹, α₁), (isfwd₂, ∆l₂⁻¹, α₂)))
+        keep, ptrs, cc = coefs(∆l⁻¹)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        GC.@preserve keep check(ccall((:sgc_op_create_curl, LIB), Cint,
+            (Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Int64}, Ptr{Cint}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cint}, Ptr{Cdouble}, Ptr{Cint}, Cint,
+             Ptr{Cint}, Cint, Ptr{Cint}, Ptr{Cdouble}),
+            h, dtype_code(T), 3, N, cints(isfwd), ptrs, cc, cints(isbloch), pairs(e⁻ⁱᵏᴸ), cints(1:3), 3, cints(1:3), 3, cints(1:3), pair(α)))
+        ops[q] = h[]
+    end
+    try
+        check(ccall((:sgc_op_apply_curlcurl, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}),
+                    ops[2], ops[1], G.ptr, F.ptr, opcode(Val(OP)), C_NULL))
+        check(ccall((:sgc_stream_sync, LIB), Cint, (Ptr{Cvoid},), C_NULL))
+    finally
+        for h in ops
+            h == C_NULL || ccall((:sgc_op_destroy, LIB), Cint, (Ptr{Cvoid},), h)
+        end
+    end
+    return nothing
+end
+
 # apply_divg! / apply_grad!  — src/matrixfree/differential/divergence.jl:41-49, gradient.jl:41-49
 for (fn, sym) in ((:apply_divg!, :sgc_apply_divg), (:apply_grad!, :sgc_apply_grad))
     @eval function $fn(A::DeviceArray{T}, B::DeviceArray{T}, ::Val{OP}, isfwd, ∆l⁻¹::NTuple{K,AbstractVector{<:Number}},
