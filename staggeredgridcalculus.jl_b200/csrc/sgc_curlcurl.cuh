@@ -363,40 +363,76 @@ SGC_D PosConst<C> pos_const(const int *fwd, const int *bc_lo, const int *bc_hi, 
     return r;
 }
 
-// the six ∂ terms with every boundary rule; kept out of line so that the registers of the
-// straight-line path are not sized by this (rarely executed) code
-template <typename T>
-struct SixTerms { T d[6]; };
-template <typename T, typename C, bool FZ>
-__device__ __noinline__ SixTerms<T> curl_point_general(PosConst<C> b, bool fx, bool fy, C cz, int zk, bool zl0, const cplx *e,
-                                                        const int *e_real, T xlo, T xhi, T ylo, T yhi, T zc, T x_yn, T z_yn, T y_xn,
-                                                        T z_xn) {
-    const T xc = FZ ? xlo : xhi, yc = FZ ? ylo : yhi;
-    const C cy = fy ? b.cys : neg(b.cys), cx = fx ? b.cxs : neg(b.cxs);
-    const int xk = b.flags & 3, yk = (b.flags >> 2) & 3;
-    const bool xl0 = (b.flags & 16) != 0, yl0 = (b.flags & 32) != 0;
-    SixTerms<T> r;
-    r.d[0] = dterm<T, C>(FZ, zk, zl0, cz, xc, FZ ? xhi : xlo, e[2], e_real[2]);
-    r.d[1] = dterm<T, C>(FZ, zk, zl0, cz, yc, FZ ? yhi : ylo, e[2], e_real[2]);
-    r.d[2] = dterm<T, C>(fy, yk, yl0, cy, xc, x_yn, e[1], e_real[1]);
-    r.d[3] = dterm<T, C>(fy, yk, yl0, cy, zc, z_yn, e[1], e_real[1]);
-    r.d[4] = dterm<T, C>(fx, xk, xl0, cx, yc, y_xn, e[0], e_real[0]);
-    r.d[5] = dterm<T, C>(fx, xk, xl0, cx, zc, z_xn, e[0], e_real[0]);
-    return r;
+// ---- shared-memory access with 32-bit addresses and immediate offsets ------------------------------
+template <int OFF>
+SGC_D cplx lds_at(unsigned a, cplx) {
+    double x, y;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2+%3];" : "=d"(x), "=d"(y) : "r"(a), "n"(OFF));
+    return cplx{x, y};
+}
+template <int OFF>
+SGC_D double lds_at(unsigned a, double) {
+    double x;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(x) : "r"(a), "n"(OFF));
+    return x;
+}
+template <int OFF>
+SGC_D void sts_at(unsigned a, cplx v) {
+    asm volatile("st.shared.v2.f64 [%0+%1], {%2,%3};" ::"r"(a), "n"(OFF), "d"(v.re), "d"(v.im) : "memory");
+}
+template <int OFF>
+SGC_D void sts_at(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0+%1], %2;" ::"r"(a), "n"(OFF), "d"(v) : "memory");
+}
+SGC_D void cp_async_to(unsigned dst, const cplx *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+SGC_D void cp_async_to(unsigned dst, const double *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
 
-// curl at one point from staged values; FZ = z-direction; `fast`: no boundary rule applies
-template <typename T, typename C, bool FZ>
-SGC_D void curl_point(bool fast, const PosConst<C> &b, bool fx, bool fy, C cz, int zk, bool zl0, const cplx *e, const int *e_real,
-                      T xlo, T xhi, T ylo, T yhi, T zc, T x_yn, T z_yn, T y_xn, T z_xn, T &d0, T &d1, T &d2, T &d3, T &d4, T &d5) {
-    const T xc = FZ ? xlo : xhi, yc = FZ ? ylo : yhi;
-    if (fast) {
-        d0 = mul(cz, sub(xhi, xlo)); d1 = mul(cz, sub(yhi, ylo));          // ∂zFx, ∂zFy
-        d2 = mul(b.cys, sub(x_yn, xc)); d3 = mul(b.cys, sub(z_yn, zc));    // ∂yFx, ∂yFz
-        d4 = mul(b.cxs, sub(y_xn, yc)); d5 = mul(b.cxs, sub(z_xn, zc));    // ∂xFy, ∂xFz
+// boundary rules as operand fix-ups for the two terms of one axis (the `dterm` rules, applied to
+// the operands so that the arithmetic afterwards is the straight-line  (±c)·(nb − cur)):
+//   forward : Bloch edge nb ← e·nb, symmetric edge nb ← 0, symmetric first cell cur ← 0
+//   backward: Bloch edge nb ← nb/e, symmetric edge: the terms are zero
+template <typename T>
+SGC_D void fix_axis(bool fwd, int kind, bool lo_zero, cplx e, int e_real, T &curA, T &nbA, T &curB, T &nbB, bool &zero) {
+    const T Z = zero_of(T{});
+    if (fwd) {
+        if (kind == 1) { nbA = mul_e(e, nbA, e_real); nbB = mul_e(e, nbB, e_real); }
+        else if (kind == 2) { nbA = Z; nbB = Z; }
+        if (lo_zero) { curA = Z; curB = Z; }
     } else {
-        const SixTerms<T> r = curl_point_general<T, C, FZ>(b, fx, fy, cz, zk, zl0, e, e_real, xlo, xhi, ylo, yhi, zc, x_yn, z_yn, y_xn, z_xn);
-        d0 = r.d[0]; d1 = r.d[1]; d2 = r.d[2]; d3 = r.d[3]; d4 = r.d[4]; d5 = r.d[5];
+        if (kind == 1) { nbA = div_e(nbA, e, e_real); nbB = div_e(nbB, e, e_real); }
+        else if (kind == 2) zero = true;
+    }
+}
+
+// The six ∂ terms of a curl at one point.  flags: bits 0-1 xk, 2-3 yk, 4 xl0, 5 yl0, 8-9 zk, 10 zl0
+// (0 for every point that no boundary rule touches: one predictable branch).
+template <typename T, typename C, bool FZ>
+SGC_D void curl_point(int flags, C cxs, C cys, bool fx, bool fy, C cz, const cplx *e, const int *e_real, T xlo, T xhi, T ylo, T yhi,
+                      T zc, T x_yn, T z_yn, T y_xn, T z_xn, T &d0, T &d1, T &d2, T &d3, T &d4, T &d5) {
+    const T Z = zero_of(T{});
+    T xc_y = FZ ? xlo : xhi, yc_x = FZ ? ylo : yhi, zc_y = zc, zc_x = zc;
+    bool z0 = false, y0 = false, x0 = false;
+    if (flags) {
+        const int zk = (flags >> 8) & 3, yk = (flags >> 2) & 3, xk = flags & 3;
+        const bool zl0 = (flags & 1024) != 0, yl0 = (flags & 32) != 0, xl0 = (flags & 16) != 0;
+        if (zk | (int)zl0) {
+            if (FZ) fix_axis<T>(true, zk, zl0, e[2], e_real[2], xlo, xhi, ylo, yhi, z0);
+            else fix_axis<T>(false, zk, false, e[2], e_real[2], xhi, xlo, yhi, ylo, z0);
+        }
+        if (yk | (int)yl0) fix_axis<T>(fy, yk, yl0, e[1], e_real[1], xc_y, x_yn, zc_y, z_yn, y0);
+        if (xk | (int)xl0) fix_axis<T>(fx, xk, xl0, e[0], e_real[0], yc_x, y_xn, zc_x, z_xn, x0);
+    }
+    d0 = mul(cz, sub(xhi, xlo)); d1 = mul(cz, sub(yhi, ylo));    // ∂zFx, ∂zFy
+    d2 = mul(cys, sub(x_yn, xc_y)); d3 = mul(cys, sub(z_yn, zc_y));  // ∂yFx, ∂yFz
+    d4 = mul(cxs, sub(y_xn, yc_x)); d5 = mul(cxs, sub(z_xn, zc_x));  // ∂xFy, ∂xFz
+    if (flags) {
+        if (z0) { d0 = Z; d1 = Z; }
+        if (y0) { d2 = Z; d3 = Z; }
+        if (x0) { d4 = Z; d5 = Z; }
     }
 }
 
@@ -407,12 +443,14 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
     constexpr int NT = 32 * (TY + 1);
     constexpr int HX = TX + 1, HY = TY + 1, EX = TX + 2, EY = TY + 2;
     constexpr int HCOMP = HX * HY, ECOMP = EX * EY;
-    constexpr int ESTAGE = 3 * ECOMP, HSTAGE = 3 * HCOMP;
+    constexpr int ES = (int)sizeof(T);
+    constexpr int ECB = ECOMP * ES, HCB = HCOMP * ES;        // bytes per component tile
+    constexpr int ESTAGE = 3 * ECB, HSTAGE = 3 * HCB;         // bytes per ring stage
     constexpr int NLD = (ECOMP + NT - 1) / NT;
     static_assert(HY <= 32, "the extra column is handled by one warp");
     extern __shared__ __align__(16) unsigned char sgc_smem_raw[];
-    T *const sE = reinterpret_cast<T *>(sgc_smem_raw);
-    T *const sH = sE + SE * ESTAGE;
+    const unsigned sE = (unsigned)__cvta_generic_to_shared(sgc_smem_raw);
+    const unsigned sH = sE + SE * ESTAGE;
 
     const int lane = threadIdx.x, w = threadIdx.y;
     const int tid = w * 32 + lane;
@@ -425,13 +463,11 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
     const int hx0 = i0 + min(0, s2x), hy0 = j0 + min(0, s2y);
     const int ex0 = hx0 + min(0, s1x), ey0 = hy0 + min(0, s1y);
     const T Z = zero_of(T{});
-    const bool tile_plain = (hx0 >= 1) && (hx0 + HX - 1 <= Nx - 2) && (hy0 >= 1) && (hy0 + HY - 1 <= Ny - 2);
     const bool lo_ext = (p.ghost_lo[0] != nullptr), hi_ext = (p.ghost_hi[0] != nullptr);
     const int ox1 = s1x < 0 ? 1 : 0, oy1 = s1y < 0 ? 1 : 0;
-    const int e_dx = s1x, e_dy = s1y * EX;
 
     // ---- loader duty ------------------------------------------------------------------------------
-    int ld_g[NLD];  // element offset inside a plane (fits 32 bits: Nx·Ny < 2^31 is checked on the host)
+    int ld_g[NLD];  // element offset inside a plane (Nx·Ny < 2^31 is checked on the host), −1: no duty
 #pragma unroll
     for (int u = 0; u < NLD; ++u) {
         const int q = tid + u * NT;
@@ -439,28 +475,27 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
         ld_g[u] = (q < ECOMP) ? wrap_index(ey0 + py, Ny) * Nx + wrap_index(ex0 + px, Nx) : -1;
     }
     // ---- role B: H position (row w, column lane) -----------------------------------------------------
-    const int qa = (w + oy1) * EX + (lane + ox1);  // E-tile index of the position
-    const int pa = w * HX + lane;                  // H-tile index
     const PosConst<C> ca = pos_const<C>(p.fwd1, p.bc1_lo, p.bc1_hi, p.c1, wrap_index(hx0 + lane, Nx), wrap_index(hy0 + w, Ny), Nx, Ny);
-    T axlo = Z, aylo = Z;
-    // ---- second role -------------------------------------------------------------------------------------
+    const unsigned a_q = (unsigned)(((w + oy1) * EX + (lane + ox1)) * ES);  // byte offset of the position in an E tile
+    const unsigned a_out = sH + (unsigned)((w * HX + lane) * ES);           // its slot in H stage 0
+    const int e_dxb = s1x * ES, e_dyb = s1y * EX * ES;
+    // ---- second role: D (warps < TY) or B′ (warp TY, lanes < HY) ----------------------------------------
     const bool roleD = (w < TY);
     const bool roleB2 = (w == TY) && (lane < HY);
-    int qb;  // D: H-tile index of the cell;  B′: E-tile index of the position
-    PosConst<C> cb;
     const int i = i0 + lane, j = j0 + w;
     const bool valid = roleD && (i < Nx) && (j < Ny);
+    PosConst<C> cb;
+    unsigned b_q, b_out = 0;
     if (roleD) {
-        qb = (w + (s2y < 0 ? 1 : 0)) * HX + (lane + (s2x < 0 ? 1 : 0));
+        b_q = (unsigned)(((w + (s2y < 0 ? 1 : 0)) * HX + (lane + (s2x < 0 ? 1 : 0))) * ES);  // the cell in an H tile
         cb = pos_const<C>(p.fwd2, p.bc2_lo, p.bc2_hi, p.c2, valid ? i : 0, valid ? j : 0, Nx, Ny);
     } else {
         const int py = roleB2 ? lane : 0;
-        qb = (py + oy1) * EX + (TX + ox1);
+        b_q = (unsigned)(((py + oy1) * EX + (TX + ox1)) * ES);
+        b_out = sH + (unsigned)((py * HX + TX) * ES);
         cb = pos_const<C>(p.fwd1, p.bc1_lo, p.bc1_hi, p.c1, wrap_index(hx0 + TX, Nx), wrap_index(hy0 + py, Ny), Nx, Ny);
     }
-    const int pb = (roleB2 ? lane : 0) * HX + TX;  // H-tile index of the B′ position
-    const int h_dx = s2x, h_dy = s2y * HX;
-    T bxlo = Z, bylo = Z;
+    const int h_dxb = s2x * ES, h_dyb = s2y * HX * ES;
 
     const int k0 = p.k_begin + blockIdx.z * p.march;
     const int k1 = min(k0 + p.march, p.k_end);
@@ -470,7 +505,8 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
     const int eb = hb + min(0, s1z);
 
     // ---- producer ------------------------------------------------------------------------------------------
-    int jj_issue = 0, stage_issue = 0;
+    int jj_issue = 0;
+    unsigned st_issue = sE + (unsigned)(tid * ES);
     auto issue = [&]() {
         if (jj_issue <= n + 1) {
             const int ke = eb + jj_issue;
@@ -485,47 +521,47 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
                 s0 = p.F[0] + off; s1 = p.F[1] + off; s2 = p.F[2] + off;
             }
             const bool centre = FZ1 ? (jj_issue <= n) : (jj_issue >= 1);
-            T *st = sE + stage_issue * ESTAGE + tid;
 #pragma unroll
             for (int u = 0; u < NLD; ++u) {
                 if (ld_g[u] >= 0) {
-                    cp_async_elem(st + u * NT, s0 + ld_g[u]);
-                    cp_async_elem(st + ECOMP + u * NT, s1 + ld_g[u]);
-                    if (centre) cp_async_elem(st + 2 * ECOMP + u * NT, s2 + ld_g[u]);
+                    cp_async_to(st_issue + u * NT * ES, s0 + ld_g[u]);
+                    cp_async_to(st_issue + u * NT * ES + ECB, s1 + ld_g[u]);
+                    if (centre) cp_async_to(st_issue + u * NT * ES + 2 * ECB, s2 + ld_g[u]);
                 }
             }
         }
         cp_async_commit();
         ++jj_issue;
-        stage_issue = (stage_issue + 1 == SE) ? 0 : stage_issue + 1;
+        st_issue += ESTAGE;
+        if (st_issue >= sE + (unsigned)(SE * ESTAGE)) st_issue -= SE * ESTAGE;
     };
 #pragma unroll
     for (int q = 0; q < SE; ++q) issue();
     cp_async_wait<SE - 2>();
     __syncthreads();
 
-    int est_lo = 0;  // ring stage of E slot m
-    int hst = 0;     // H stage of slot m  (m % 3)
+    unsigned e_lo = sE;      // ring stage of E slot m
+    unsigned h_cur = 0;      // byte offset of the H stage of slot m
     int64_t off_out = (int64_t)k0 * sz + (int64_t)j * sy + i;
+    // the carried "lo" plane values: E slot 0 for the H positions, H slot 0 for the output cell (set at m = 2)
+    T axlo = lds_at<0>(e_lo + a_q, T{}), aylo = lds_at<ECB>(e_lo + a_q, T{});
+    T bxlo = Z, bylo = Z;
+    if (!roleD) { bxlo = lds_at<0>(e_lo + b_q, T{}); bylo = lds_at<ECB>(e_lo + b_q, T{}); }
 
     // one H value from the staged E planes (role B and role B′ share this)
-    auto h_point = [&](int m, int q, const PosConst<C> &c, T &xlo_c, T &ylo_c, int pos, bool fast, C cz, int zk, bool zl0) {
-        const int est_hi = (est_lo + 1 == SE) ? 0 : est_lo + 1;
-        const T *slo = sE + est_lo * ESTAGE;
-        const T *shi = sE + est_hi * ESTAGE;
-        const T *sc = FZ1 ? slo : shi;
-        if (m == 0) { xlo_c = slo[q]; ylo_c = slo[ECOMP + q]; }
-        const T xhi = shi[q], yhi = shi[ECOMP + q];
-        const T zc = sc[2 * ECOMP + q];
-        const T x_yn = sc[q + e_dy], z_yn = sc[2 * ECOMP + q + e_dy];
-        const T y_xn = sc[ECOMP + q + e_dx], z_xn = sc[2 * ECOMP + q + e_dx];
+    auto h_point = [&](unsigned q, const PosConst<C> &c, T &xlo_c, T &ylo_c, unsigned out, int zflags, C cz, unsigned e_hi) {
+        const unsigned ahi = e_hi + q;
+        const unsigned ac = (FZ1 ? e_lo : e_hi) + q;
+        const T xhi = lds_at<0>(ahi, T{}), yhi = lds_at<ECB>(ahi, T{});
+        const T zc = lds_at<2 * ECB>(ac, T{});
+        const T x_yn = lds_at<0>(ac + e_dyb, T{}), z_yn = lds_at<2 * ECB>(ac + e_dyb, T{});
+        const T y_xn = lds_at<ECB>(ac + e_dxb, T{}), z_xn = lds_at<2 * ECB>(ac + e_dxb, T{});
         T d0, d1, d2, d3, d4, d5;
-        curl_point<T, C, FZ1>(fast, c, fx1, fy1, cz, zk, zl0, p.e1, p.e1_real, xlo_c, xhi, ylo_c, yhi, zc, x_yn, z_yn, y_xn, z_xn,
-                              d0, d1, d2, d3, d4, d5);
-        T *hout = sH + hst * HSTAGE + pos;
-        hout[0] = add(add(Z, neg(d1)), d3);  // Gv .= 0 ; += (−∂zFy) ; += ∂yFz   (curl.jl:66-91)
-        hout[HCOMP] = add(d0, neg(d5));
-        hout[2 * HCOMP] = add(neg(d2), d4);
+        curl_point<T, C, FZ1>(c.flags | zflags, c.cxs, c.cys, fx1, fy1, cz, p.e1, p.e1_real, xlo_c, xhi, ylo_c, yhi, zc, x_yn, z_yn, y_xn,
+                              z_xn, d0, d1, d2, d3, d4, d5);
+        sts_at<0>(out + h_cur, add(add(Z, neg(d1)), d3));  // Gv .= 0 ; += (−∂zFy) ; += ∂yFz   (curl.jl:66-91)
+        sts_at<HCB>(out + h_cur, add(d0, neg(d5)));
+        sts_at<2 * HCB>(out + h_cur, add(neg(d2), d4));
         xlo_c = xhi;
         ylo_c = yhi;
     };
@@ -535,52 +571,58 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
         if (m >= 1) issue();  // E slot m − 1 + SE → the stage slot m − 1 used (free since the last barrier)
         if (m <= n) {
             // ================= B(m), B′(m): H plane hb + m =============================================
-            const bool ghostH = (hk < 0 && lo_ext) || (hk >= Nz && hi_ext);
-            const int kk = ghostH ? hk : ((hk >= 0 && hk < Nz) ? hk : wrap_index(hk, Nz));
-            const C cz = ghostH ? (hk < 0 ? p.c1z_lo : p.c1z_hi) : p.c1[2][kk];
-            int zk = 0;
-            bool zl0 = false, ghost_plain = false;
-            if (ghostH) {
-                const int side = (hk < 0) ? p.bc1_lo[2] : p.bc1_hi[2];
-                if (side == BC_BLOCH) zk = 1;
-                else ghost_plain = true;
-            } else if (FZ1) {
-                if (kk == Nz - 1) zk = (p.bc1_hi[2] == BC_BLOCH) ? 1 : (p.bc1_hi[2] == BC_SYM ? 2 : 0);
-                zl0 = (kk == 0) && (p.bc1_lo[2] == BC_SYM);
-            } else if (kk == 0) {
-                zk = (p.bc1_lo[2] == BC_BLOCH) ? 1 : (p.bc1_lo[2] == BC_SYM ? 2 : 0);
+            int zflags = 0;
+            C cz;
+            if (hk > 0 && hk < Nz - 1) {
+                cz = p.c1[2][hk];
+            } else {
+                const bool ghostH = (hk < 0 && lo_ext) || (hk >= Nz && hi_ext);
+                const int kk = ghostH ? hk : wrap_index(hk, Nz);
+                cz = ghostH ? (hk < 0 ? p.c1z_lo : p.c1z_hi) : p.c1[2][kk];
+                if (ghostH) {
+                    const int side = (hk < 0) ? p.bc1_lo[2] : p.bc1_hi[2];
+                    if (side == BC_BLOCH) zflags = 1 << 8;
+                } else if (FZ1) {
+                    if (kk == Nz - 1) zflags = ((p.bc1_hi[2] == BC_BLOCH) ? 1 : (p.bc1_hi[2] == BC_SYM ? 2 : 0)) << 8;
+                    if (kk == 0 && p.bc1_lo[2] == BC_SYM) zflags |= 1024;
+                } else if (kk == 0) {
+                    zflags = ((p.bc1_lo[2] == BC_BLOCH) ? 1 : (p.bc1_lo[2] == BC_SYM ? 2 : 0)) << 8;
+                }
             }
-            const bool fast = tile_plain && (ghostH ? ghost_plain : (kk > 0 && kk < Nz - 1));
-            h_point(m, qa, ca, axlo, aylo, pa, fast, cz, zk, zl0);
-            if (roleB2) h_point(m, qb, cb, bxlo, bylo, pb, fast, cz, zk, zl0);
+            unsigned e_hi = e_lo + ESTAGE;
+            if (e_hi >= sE + (unsigned)(SE * ESTAGE)) e_hi = sE;
+            h_point(a_q, ca, axlo, aylo, a_out, zflags, cz, e_hi);
+            if (roleB2) h_point(b_q, cb, bxlo, bylo, b_out, zflags, cz, e_hi);
+            e_lo = e_hi;
         }
         if (roleD && m >= 2) {
             // ================= D(m − 2): output plane k0 + m − 2 from H slots m − 2 (lo), m − 1 (hi) =======
             const int k = k0 + m - 2;
             T g0 = Z, g1 = Z, g2 = Z;
             if (ADD && valid) { g0 = ldg_plain(p.G[0] + off_out); g1 = ldg_plain(p.G[1] + off_out); g2 = ldg_plain(p.G[2] + off_out); }
-            const int st_hi = (hst == 0) ? 2 : hst - 1;     // slot m − 1
-            const int st_lo = (st_hi == 0) ? 2 : st_hi - 1;  // slot m − 2
-            const T *hlo = sH + st_lo * HSTAGE;
-            const T *hhi = sH + st_hi * HSTAGE;
-            const T *hc = FZ2 ? hlo : hhi;
-            if (m == 2) { bxlo = hlo[qb]; bylo = hlo[HCOMP + qb]; }
-            const T xhi = hhi[qb], yhi = hhi[HCOMP + qb];
-            const T zc = hc[2 * HCOMP + qb];
-            const T x_yn = hc[qb + h_dy], z_yn = hc[2 * HCOMP + qb + h_dy];
-            const T y_xn = hc[HCOMP + qb + h_dx], z_xn = hc[2 * HCOMP + qb + h_dx];
+            // h_cur is the stage of slot m (also at m = n + 1); slots m − 1 and m − 2 precede it in the ring
+            const unsigned st_hi = (h_cur == 0) ? 2u * HSTAGE : h_cur - HSTAGE;            // slot m − 1
+            const unsigned st_lo = (st_hi == 0) ? 2u * HSTAGE : st_hi - HSTAGE;           // slot m − 2
+            const unsigned ahi = sH + st_hi + b_q, alo = sH + st_lo + b_q;
+            const unsigned ac = FZ2 ? alo : ahi;
+            if (m == 2) { bxlo = lds_at<0>(alo, T{}); bylo = lds_at<HCB>(alo, T{}); }
+            const T xhi = lds_at<0>(ahi, T{}), yhi = lds_at<HCB>(ahi, T{});
+            const T zc = lds_at<2 * HCB>(ac, T{});
+            const T x_yn = lds_at<0>(ac + h_dyb, T{}), z_yn = lds_at<2 * HCB>(ac + h_dyb, T{});
+            const T y_xn = lds_at<HCB>(ac + h_dxb, T{}), z_xn = lds_at<2 * HCB>(ac + h_dxb, T{});
             const C cz = p.c2[2][k];
-            int zk = 0;
-            bool zl0 = false;
-            if (FZ2) {
-                if (k == Nz - 1) zk = (p.bc2_hi[2] == BC_BLOCH) ? 1 : (p.bc2_hi[2] == BC_SYM ? 2 : 0);
-                zl0 = (k == 0) && (p.bc2_lo[2] == BC_SYM);
-            } else if (k == 0) {
-                zk = (p.bc2_lo[2] == BC_BLOCH) ? 1 : (p.bc2_lo[2] == BC_SYM ? 2 : 0);
+            int zflags = 0;
+            if (k == 0 || k == Nz - 1) {
+                if (FZ2) {
+                    if (k == Nz - 1) zflags = ((p.bc2_hi[2] == BC_BLOCH) ? 1 : (p.bc2_hi[2] == BC_SYM ? 2 : 0)) << 8;
+                    if (k == 0 && p.bc2_lo[2] == BC_SYM) zflags |= 1024;
+                } else if (k == 0) {
+                    zflags = ((p.bc2_lo[2] == BC_BLOCH) ? 1 : (p.bc2_lo[2] == BC_SYM ? 2 : 0)) << 8;
+                }
             }
             T d0, d1, d2, d3, d4, d5;
-            curl_point<T, C, FZ2>(tile_plain && k > 0 && k < Nz - 1, cb, fx2, fy2, cz, zk, zl0, p.e2, p.e2_real, bxlo, xhi, bylo, yhi, zc,
-                                  x_yn, z_yn, y_xn, z_xn, d0, d1, d2, d3, d4, d5);
+            curl_point<T, C, FZ2>(cb.flags | zflags, cb.cxs, cb.cys, fx2, fy2, cz, p.e2, p.e2_real, bxlo, xhi, bylo, yhi, zc, x_yn, z_yn,
+                                  y_xn, z_xn, d0, d1, d2, d3, d4, d5);
             T gx, gy, gz;
             if (ADD) { gx = add(add(g0, neg(d1)), d3); gy = add(add(g1, d0), neg(d5)); gz = add(add(g2, neg(d2)), d4); }
             else     { gx = add(add(Z, neg(d1)), d3);  gy = add(d0, neg(d5));          gz = add(neg(d2), d4); }
@@ -593,10 +635,7 @@ __global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_co
             bylo = yhi;
             off_out += sz;
         }
-        if (m <= n) {
-            est_lo = (est_lo + 1 == SE) ? 0 : est_lo + 1;
-            hst = (hst == 2) ? 0 : hst + 1;
-        }
+        if (m <= n) h_cur = (h_cur == 2u * HSTAGE) ? 0u : h_cur + HSTAGE;
         cp_async_wait<SE - 3>();  // E slot m + 2 has landed (for this thread) …
         __syncthreads();          // … and for everybody; H plane m is complete; E slot m is free
     }
