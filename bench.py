@@ -184,6 +184,7 @@ def main():
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="side experiments only: skip the host-array leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="z-chunks of the host-array pipeline")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] (2-D operators) and fused curl-of-curl side measurements")
     ap.add_argument("--serial-e2e", action="store_true", help="N > 1: H2D, step, D2H without the chunked pipeline")
     args = ap.parse_args()
@@ -199,6 +200,9 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # keep stdout for the ONE JSON line: NCCL's banner ("NCCL version …", printed at NCCL_DEBUG=VERSION/WARN) and
+    # any NCCL warning go to a per-process log file instead of stdout
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
     import torch
     import torch.distributed as dist
     import sgc_b200 as S
@@ -325,7 +329,7 @@ def main():
         e2e_step, e2e_mode = e2e_step_serial, "serial: H2D, 2 curls, D2H"
         if world == 1:  # z-chunked duplex pipeline (copies in, kernels and copies out overlap)
             from sgc_b200.hostpipe import HostCurlCurl
-            pipe = HostCurlCurl(c_dual.backend.op, c_prim.backend.op, NLOCAL, nchunks=16)
+            pipe = HostCurlCurl(c_dual.backend.op, c_prim.backend.op, NLOCAL, nchunks=args.e2e_chunks)
             ref_out = None
             e2e_step_serial()
             ref_out = Out_host.clone()
@@ -334,10 +338,10 @@ def main():
             if not torch.equal(ref_out, Out_host):
                 raise RuntimeError("pipelined host path disagrees with the serial host path")
             e2e_step = lambda: pipe.run(E_host, Out_host)
-            e2e_mode = "z-chunked (16) full-duplex pipeline: H2D | 2 fused curls per chunk | D2H on three streams"
+            e2e_mode = f"z-chunked ({args.e2e_chunks}) full-duplex pipeline: H2D | 2 fused curls per chunk | D2H on three streams"
         elif arena is not None and not args.serial_e2e:  # the same pipeline per rank; interface planes after a peer barrier
             from sgc_b200.hostpipe import HostSlabCurlCurl
-            pipe = HostSlabCurlCurl(c_dual, c_prim, E, H, E2, nchunks=16)
+            pipe = HostSlabCurlCurl(c_dual, c_prim, E, H, E2, nchunks=args.e2e_chunks)
             e2e_step_serial()
             ref_out = Out_host.clone()
             Out_host.zero_()
@@ -345,7 +349,7 @@ def main():
             if not torch.equal(ref_out, Out_host):
                 raise RuntimeError("pipelined slab host path disagrees with the serial host path")
             e2e_step = lambda: pipe.run(E_host, Out_host)
-            e2e_mode = ("per-rank z-chunked (16) full-duplex pipeline, interface planes after a peer barrier; "
+            e2e_mode = (f"per-rank z-chunked ({args.e2e_chunks}) full-duplex pipeline, interface planes after a peer barrier; "
                         f"process bound to the GPU's NUMA node ({'yes' if numa_cpus else 'topology not exposed'})")
 
         e2e_steps = max(3, min(args.steps, 10))
@@ -362,6 +366,12 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e_val = 2 * M * world * e2e_steps / e2e_s / 1e9
+
+    # BASELINE configs[3] at N > 1: the 512^3 create_curl row-partitioned into per-GPU CSC blocks
+    asm_part = None
+    if world > 1 and not args.no_assembly:
+        E_host = Out_host = None
+        asm_part = bench_assembly_partitioned(S, torch, dist, rank, world)
 
     if rank != 0:
         if world > 1:
@@ -407,6 +417,8 @@ def main():
     if world == 1 and not args.no_extras:
         E_host = Out_host = None  # release the pinned staging arrays
         out["other_configs"] = bench_other_configs(S, torch, peak, c_dual.backend.op, c_prim.backend.op, E, E2, ms_step)
+    if world > 1 and not args.no_assembly:
+        out["assembly"] = asm_part
     if world == 1 and not args.no_cpu_baseline:
         rate, threads, sample = cpu_reference_rate(dprim, ddual, NLOCAL[2], args.cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
@@ -469,6 +481,58 @@ def bench_assembly(S, torch, peak, cplx=False):
     except Exception as ex:  # out of memory on a shared box etc.
         res = {"error": str(ex)[:200]}
     return res
+
+
+def bench_assembly_partitioned(S, torch, dist, rank, world):
+    """512³ Float64 all-Bloch create_curl, row-partitioned: rank r assembles the CSC block of its contiguous
+    row range (own colptr of length n+1; the blocks stack to the global matrix).  No exchange; the time is the
+    max over ranks, the rate the whole matrix's nnz over that time."""
+    import ctypes as C
+    from sgc_b200._lib import lib, check
+    from sgc_b200.device import ints, int64s, scalars2, stream_handle
+    from sgc_b200.slab import row_range_for_rank
+    n = 512
+    N, M = (n, n, n), n ** 3
+    try:
+        h = C.c_void_p()
+        check(lib.sgc_asm_create_curl(C.byref(h), 3, int64s(N), ints([1, 1, 1]), None, 0, ints([1, 1, 1]),
+                                      scalars2([1.0] * 3), 0, ints([1, 2, 3]), 3, ints([1, 2, 3]), 3, ints([1, 2, 3]), 1))
+        r0, r1 = row_range_for_rank(3 * M, rank, world)
+        st = stream_handle()
+        nnz = C.c_int64()
+        check(lib.sgc_asm_set_row_range(h, r0, r1))
+        check(lib.sgc_asm_count(h, C.byref(nnz), st))
+        colptr = torch.empty(3 * M + 1, dtype=torch.int64, device="cuda")
+        rowval = torch.empty(nnz.value, dtype=torch.int64, device="cuda")
+        nzval = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
+
+        def once():
+            check(lib.sgc_asm_set_row_range(h, r0, r1))  # drops the cached count: time the whole assembly
+            check(lib.sgc_asm_count(h, C.byref(nnz), st))
+            check(lib.sgc_asm_fill_all(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()),
+                                       C.c_void_p(nzval.data_ptr()), st))
+        for _ in range(2):
+            once()
+        torch.cuda.synchronize()
+        dist.barrier()
+        reps = 5
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(reps):
+            once()
+        ev1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / reps, float(nnz.value)], device="cuda", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        lib.sgc_asm_destroy(h)
+        ms, total = float(tmax[0]), int(t[1])
+        return {"workload": f"create_curl 512^3 Float64 all-Bloch, row-partitioned into {world} per-GPU CSC blocks (no exchange)",
+                "nnz": total, "ms": ms, "nnz_per_s": total / (ms * 1e-3), "nnz_ok": total == 12 * M,
+                "includes": "per rank: count pass + device scan + nnz read-back + single fill pass (max over ranks)"}
+    except Exception as ex:
+        return {"error": str(ex)[:200]}
 
 
 def _time(torch, fn, iters=10, warm=3):

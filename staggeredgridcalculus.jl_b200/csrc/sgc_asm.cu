@@ -340,6 +340,15 @@ static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
     }
     p.cols_per_group = a->cmpfirst ? a->Kin : 1;
     p.ngroups = a->cmpfirst ? a->M : (int64_t)a->Kin * a->M;
+    p.skip_enabled = 0;
+    if (a->cmpfirst && !(a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M)) {
+        const int64_t span = a->M / a->N[a->ndim - 1];  // cells per hyper-plane of the slowest axis = longest reach
+        const int64_t c0 = a->row_begin / a->Kout, c1 = (a->row_end + a->Kout - 1) / a->Kout;
+        p.skip_enabled = 1;
+        p.near_lo = std::max<int64_t>(c0 - span, 0);
+        p.near_hi = std::min<int64_t>(c1 + span, a->M);
+        p.wrap_span = span;
+    }
     p.prefix_enabled = (a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M && a->prefix_tables && !a->force_count_pass) ? 1 : 0;
     int64_t before = 0;
     for (int set = 0; set < 4; ++set) {

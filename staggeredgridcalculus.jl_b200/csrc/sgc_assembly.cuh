@@ -51,6 +51,11 @@ struct AsmParams {
     // closed-form entry offsets (all rows kept): the per-column count is separable,
     // count = a(i) + b(j) + c(k), so the number of entries before a cell is a closed form of the
     // prefix sums PA, PB, PC.  Set s = nu (block ordering) or 3 (all block columns summed).
+    // row partition, component-major ordering: only the columns of cells within one z-plane (the
+    // longest stencil reach) of the kept rows' cells, or in the first / last plane (Bloch wrap), can
+    // hold entries; CTAs entirely outside [near_lo, near_hi) and the wrap planes skip the entry work
+    int skip_enabled;
+    int64_t near_lo, near_hi, wrap_span;
     int prefix_enabled;
     const int64_t *prefix[4][3];  // [set][axis] → int64[N_axis + 1], exclusive prefix sums
     int64_t set_base[4];          // entries before the first group of the set
@@ -260,6 +265,21 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
     constexpr bool WRITES = (MODE == ASM_FILL || MODE == ASM_FILL_ALL);
     const int64_t g0 = (int64_t)blockIdx.x * BLOCK;
     const int64_t g = g0 + threadIdx.x;
+    if (p.skip_enabled) {
+        const int64_t g1 = min(g0 + (int64_t)BLOCK, p.ngroups);
+        const bool in_near = (g1 > p.near_lo) && (g0 < p.near_hi);
+        const bool in_wrap = (g0 < p.wrap_span) || (g1 > p.ngroups - p.wrap_span);
+        if (!in_near && !in_wrap) {  // no column of this CTA reaches a kept row
+            if (MODE == ASM_COUNT) {
+                if (threadIdx.x == 0) cta_total[blockIdx.x] = 0;
+            } else if (MODE == ASM_COLPTR || MODE == ASM_FILL_ALL) {
+                const int64_t v = cta_offset[blockIdx.x] + p.index_base;
+                const int64_t col0s = g0 * NCOLS;
+                for (int q = threadIdx.x; q < (int)(g1 - g0) * NCOLS; q += BLOCK) colptr_out[col0s + q] = v;
+            }
+            return;
+        }
+    }
     const bool live = g < p.ngroups;
     int nu0 = 0;
     IDX c = 0, sub[3] = {0, 0, 0};

@@ -171,6 +171,33 @@ def test_row_partition_concatenates_to_global(S):
                 assert np.array_equal(stacked.data, full.data)
 
 
+def test_row_partition_on_a_tall_grid_skips_far_columns(S):
+    """Per-rank blocks of a grid with many z-planes: most column CTAs of a rank hold no entry of its rows
+    and are skipped; the blocks must still stack to the global matrix (all-Bloch incl. the z wrap-around,
+    and a symmetric case), for curl, divergence and gradient."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(16)
+    N = (8, 4, 64)
+    M = int(np.prod(N))
+    dlinv = [rand_coef(rng, n, True) for n in N]
+    e = [np.exp(-0.1j), np.exp(-0.2j), np.exp(-0.3j)]
+    makers = [("curl", lambda **kw: S.create_curl([True, False, True], dlinv, kw.pop("isbloch"), e, index_base=0, **kw), 3 * M),
+              ("divg", lambda **kw: S.create_divg([False, True, True], dlinv, kw.pop("isbloch"), e, index_base=0, **kw), M),
+              ("grad", lambda **kw: S.create_grad([True, True, False], dlinv, kw.pop("isbloch"), e, index_base=0, **kw), 3 * M)]
+    for name, make, nrows in makers:
+        for isbloch in ([True, True, True], [True, False, False]):
+            full = make(isbloch=isbloch).to_scipy()
+            for nparts in (4, 7):
+                cuts = [round(i * nrows / nparts) for i in range(nparts + 1)]
+                blocks = [make(isbloch=isbloch, row_range=(a, b)).to_scipy() for a, b in zip(cuts[:-1], cuts[1:])]
+                stacked = sp.vstack(blocks).tocsc()
+                stacked.sort_indices()
+                what = f"{name} bloch={isbloch} parts={nparts}"
+                assert np.array_equal(stacked.indptr, full.indptr), what
+                assert np.array_equal(stacked.indices, full.indices), what
+                assert np.array_equal(stacked.data, full.data), what
+
+
 def test_matrix_times_field_equals_matrix_free(S):
     """test/curl.jl:54-57: `mul!(g, Curl, f)` ≈ `apply_curl!` (block ordering), on the device."""
     import torch
