@@ -133,52 +133,66 @@ __global__ void __launch_bounds__(256) k_term(const __grid_constant__ TermParams
 // ---------------------------------------------------------------------------------------------
 // Same formulas, evaluated from values already in registers: `nb` is the value at i+1 (forward)
 // or i−1 (backward); at the physical / slab face it is the RAW ghost value.
+// ci = c[i], wi = w[i], wn = w[i+1] (forward) / w[i−1] (backward) — every table entry the formulas of
+// element i touch (c[0], w[0], w[1] in the boundary branches are c[i], w[i], w[i+1] at i = 0).
 template <typename T, typename C, int KIND>
-SGC_D T term_eval(const TermParams<T, C> &p, int64_t i, T cur, T nb) {
+SGC_D T term_eval_c(const TermParams<T, C> &p, int64_t i, T cur, T nb, C ci, C wi, C wn) {
     const int64_t Nw = p.Nw;
     if (p.fwd) {
         if (i == Nw - 1) {
             if (p.bc_hi == BC_SYM) {
-                if (KIND == KIND_PARTIAL) return neg(mul(p.c[i], cur));
+                if (KIND == KIND_PARTIAL) return neg(mul(ci, cur));
                 if (KIND == KIND_MEAN_ARITH) return mul(p.a2, cur);
-                return mul(mul(p.c[i], p.w[i]), cur);
+                return mul(mul(ci, wi), cur);
             }
             if (p.bc_hi == BC_BLOCH) {
-                if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(mul_e(p.e, nb, p.e_real), cur));
+                if (KIND == KIND_PARTIAL) return mul(ci, sub(mul_e(p.e, nb, p.e_real), cur));
                 if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(mul_e(p.e, nb, p.e_real), cur));
-                return mul(p.c[i], add(mul(p.w_hi, nb), mul(p.w[i], cur)));
+                return mul(ci, add(mul(p.w_hi, nb), mul(wi, cur)));
             }
-            if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(nb, cur));
+            if (KIND == KIND_PARTIAL) return mul(ci, sub(nb, cur));
             if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(nb, cur));
-            return mul(p.c[i], add(mul(p.w_hi, nb), mul(p.w[i], cur)));
+            return mul(ci, add(mul(p.w_hi, nb), mul(wi, cur)));
         }
         if (i == 0 && p.bc_lo == BC_SYM) {
-            if (KIND == KIND_PARTIAL) return mul(p.c[0], nb);
+            if (KIND == KIND_PARTIAL) return mul(ci, nb);
             if (KIND == KIND_MEAN_ARITH) return mul(p.a2, nb);
-            return mul(mul(p.c[0], p.w[1]), nb);
+            return mul(mul(ci, wn), nb);
         }
-        if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(nb, cur));
+        if (KIND == KIND_PARTIAL) return mul(ci, sub(nb, cur));
         if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(nb, cur));
-        return mul(p.c[i], add(mul(p.w[i + 1], nb), mul(p.w[i], cur)));
+        return mul(ci, add(mul(wn, nb), mul(wi, cur)));
     }
     if (i == 0) {
         if (p.bc_lo == BC_SYM) {
             if (KIND == KIND_PARTIAL) return zero_of(cur);
             if (KIND == KIND_MEAN_ARITH) return mul(p.a1, cur);
-            return mul(mul(p.b0, p.w[0]), cur);
+            return mul(mul(p.b0, wi), cur);
         }
         if (p.bc_lo == BC_BLOCH) {
-            if (KIND == KIND_PARTIAL) return mul(p.c[0], sub(cur, div_e(nb, p.e, p.e_real)));
+            if (KIND == KIND_PARTIAL) return mul(ci, sub(cur, div_e(nb, p.e, p.e_real)));
             if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, div_e(nb, p.e, p.e_real)));
-            return mul(p.c[0], add(mul(p.w[0], cur), div_e(mul(p.w_lo, nb), p.e, p.e_real)));
+            return mul(ci, add(mul(wi, cur), div_e(mul(p.w_lo, nb), p.e, p.e_real)));
         }
-        if (KIND == KIND_PARTIAL) return mul(p.c[0], sub(cur, nb));
+        if (KIND == KIND_PARTIAL) return mul(ci, sub(cur, nb));
         if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, nb));
-        return mul(p.c[0], add(mul(p.w[0], cur), mul(p.w_lo, nb)));
+        return mul(ci, add(mul(wi, cur), mul(p.w_lo, nb)));
     }
-    if (KIND == KIND_PARTIAL) return mul(p.c[i], sub(cur, nb));
+    if (KIND == KIND_PARTIAL) return mul(ci, sub(cur, nb));
     if (KIND == KIND_MEAN_ARITH) return mul(p.a2, add(cur, nb));
-    return mul(p.c[i], add(mul(p.w[i], cur), mul(p.w[i - 1], nb)));
+    return mul(ci, add(mul(wi, cur), mul(wn, nb)));
+}
+template <typename T, typename C, int KIND>
+SGC_D T term_eval(const TermParams<T, C> &p, int64_t i, T cur, T nb) {
+    const int64_t Nw = p.Nw;
+    C ci{}, wi{}, wn{};
+    if (KIND != KIND_MEAN_ARITH) ci = p.c[i];
+    if (KIND == KIND_MEAN_WEIGHTED) {
+        wi = p.w[i];
+        const int64_t in = p.fwd ? i + 1 : i - 1;
+        if (in >= 0 && in < Nw) wn = p.w[in];
+    }
+    return term_eval_c<T, C, KIND>(p, i, cur, nb, ci, wi, wn);
 }
 
 // VEC consecutive elements (VEC·sizeof(T) is a multiple of 16 bytes, address 16-byte aligned)
@@ -228,6 +242,20 @@ __global__ void __launch_bounds__(256) k_term_x(const __grid_constant__ TermPara
     const bool nb_inside = (nbi >= 0 && nbi < Nw);
     const bool nb_ghost = fwd ? (p.bc_hi != BC_SYM) : (p.bc_lo != BC_SYM);
     const T Z = zero_of(T{});
+    // the table entries of my VEC elements are the same for every row: load them once
+    C ci[VEC], wi[VEC], wn[VEC];
+#pragma unroll
+    for (int e = 0; e < VEC; ++e) {
+        ci[e] = C{}; wi[e] = C{}; wn[e] = C{};
+        const int64_t i = iv + e, in = fwd ? i + 1 : i - 1;
+        if (active && i < Nw) {
+            if (KIND != KIND_MEAN_ARITH) ci[e] = p.c[i];
+            if (KIND == KIND_MEAN_WEIGHTED) {
+                wi[e] = p.w[i];
+                if (in >= 0 && in < Nw) wn[e] = p.w[in];
+            }
+        }
+    }
     for (int64_t o0 = p.o_begin + (int64_t)blockIdx.y * R; o0 < p.o_end; o0 += (int64_t)gridDim.y * R) {
         T cur[R][VEC];
         T nb[R];
@@ -257,7 +285,7 @@ __global__ void __launch_bounds__(256) k_term_x(const __grid_constant__ TermPara
 #pragma unroll
             for (int e = 0; e < VEC; ++e) {
                 const T n = fwd ? (e < VEC - 1 ? cur[r][e + 1 < VEC ? e + 1 : e] : nb[r]) : (e > 0 ? cur[r][e > 0 ? e - 1 : 0] : nb[r]);
-                out[e] = term_eval<T, C, KIND>(p, iv + e, cur[r][e], n);
+                out[e] = term_eval_c<T, C, KIND>(p, iv + e, cur[r][e], n, ci[e], wi[e], wn[e]);
             }
             T *g = p.G + (o0 + r) * Nw + iv;
             if (ADD) {
@@ -302,10 +330,18 @@ __global__ void __launch_bounds__(256) k_term_s(const __grid_constant__ TermPara
             for (int r = 0; r < R; ++r) {
                 const int64_t i = i0 + r;
                 if (i >= p.i_end) break;
+                // the table entries of row i, once for the whole vector
+                C ci{}, wi{}, wn{};
+                if (KIND != KIND_MEAN_ARITH) ci = p.c[i];
+                if (KIND == KIND_MEAN_WEIGHTED) {
+                    wi = p.w[i];
+                    const int64_t in = fwd ? i + 1 : i - 1;
+                    if (in >= 0 && in < Nw) wn = p.w[in];
+                }
                 T out[VEC];
 #pragma unroll
                 for (int e = 0; e < VEC; ++e)
-                    out[e] = term_eval<T, C, KIND>(p, i, fwd ? V[r][e] : V[r + 1][e], fwd ? V[r + 1][e] : V[r][e]);
+                    out[e] = term_eval_c<T, C, KIND>(p, i, fwd ? V[r][e] : V[r + 1][e], fwd ? V[r + 1][e] : V[r][e], ci, wi, wn);
                 T *g = p.G + (o * Nw + i) * inner + x;
                 if (ADD) {
                     T old[VEC];

@@ -400,7 +400,11 @@ static int launch_term(const sgc_op *op, const Term &t, T *G, const T *F, const 
         const bool aligned = ((uintptr_t)p.G % 16 == 0) && ((uintptr_t)p.F % 16 == 0) && (xax || (uintptr_t)p.ghost % 16 == 0);
         const int64_t len = xax ? p.Nw : p.inner;
         int vec = 0;
-        if (aligned && len % VBIG == 0) vec = VBIG;
+        // 32-byte vectors, except where 16-byte vectors measured faster on B200 (8192² Float64, tools/time_2d_v4.py):
+        // the non-accumulating contiguous-axis kernels (∂x 5.9 vs 5.6, m̂x 5.7 vs 5.1, weighted m̂x 5.3 vs 4.4 TB/s)
+        const int vmode = op->variant & 0xF;  // 4: force 16-byte, 5: force 32-byte (experiments)
+        const bool prefer_small = (vmode == 4) || (vmode != 5 && !add_mode && (xax || t.kind == KIND_MEAN_ARITH));  // (m̂y: 5.6 vs 5.3)
+        if (aligned && len % VBIG == 0 && !prefer_small) vec = VBIG;
         else if (aligned && len % VSMALL == 0) vec = VSMALL;
         const bool full_range = (p.i_begin == 0 && p.i_end == p.Nw);
         if (vec && op->variant != 3 && (!xax || (full_range && p.Nw >= 64 * vec))) {
