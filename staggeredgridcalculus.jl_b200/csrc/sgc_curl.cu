@@ -131,6 +131,65 @@ static void launch_curl3_tiles(const CurlParams<T, C> &p, int tx, int ty, dim3 g
 }
 
 
+// apply_divg! / apply_grad! on 3-D grids through the same staged z-march (k_curl3p MODE = DIVG / GRAD)
+template <typename T, typename C, bool ADD, int MODE>
+static int launch_divgrad_one(const CurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
+    constexpr int TX = 32, TY = 4, S = 6, MINB = 4;
+    constexpr size_t smem = (size_t)S * 3 * (TY + 1) * (TX + 1) * sizeof(T);
+    auto kern = k_curl3p<T, C, ADD, TX, TY, S, MINB, true, MODE>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
+    return SGC_OK;
+}
+
+template <typename T, typename C>
+int sgc_launch_divgrad3(const sgc_op *op, bool is_divg, T *G, const T *F, const void *const *ghost, bool add_mode,
+                        int64_t k_begin, int64_t k_end, cudaStream_t st) {
+    if (k_end <= k_begin) return SGC_OK;
+    CurlParams<T, C> p{};
+    const int64_t M = op->M, sz = op->N[0] * op->N[1];
+    const Term *tz = nullptr;
+    for (const Term &t : op->terms) {  // one ∂ term per axis
+        const int d = t.axis;
+        p.c[d] = (const C *)((const unsigned char *)op->arena + t.off_c);
+        p.e[d] = t.e; p.e_real[d] = t.e_real; p.fwd[d] = t.fwd;
+        p.bc_lo[d] = p.bc_hi[d] = t.bloch ? BC_BLOCH : BC_SYM;
+        if (d == 2) tz = &t;
+    }
+    if (!tz) return sgc_fail(SGC_ERR_INVALID, "divergence / gradient without a z term");
+    if (op->lo_iface) p.bc_lo[2] = BC_IFACE;
+    if (op->hi_iface) p.bc_hi[2] = BC_IFACE;
+    if (is_divg) {  // slot 0 = F_z (z-differenced), slot 1 = F_x (x-differenced), slot 2 = F_y (y-differenced)
+        p.F[0] = F + 2 * M; p.F[1] = F; p.F[2] = F + M;
+        p.G[0] = p.G[1] = p.G[2] = G;
+    } else {        // slot 0 = f
+        p.F[0] = p.F[1] = p.F[2] = F;
+        for (int d = 0; d < 3; ++d) p.G[d] = G + d * M;
+    }
+    const T *g = ghost ? (const T *)ghost[tz->in] : nullptr;
+    p.ghost[0] = g ? g : (tz->fwd ? p.F[0] : p.F[0] + (op->N[2] - 1) * sz);
+    p.ghost[1] = p.ghost[0];
+    p.Nx = (int)op->N[0]; p.Ny = (int)op->N[1]; p.Nz = (int)op->N[2];
+    p.k_begin = (int)k_begin; p.k_end = (int)k_end;
+    p.march = 12;
+    const int64_t nk = k_end - k_begin;
+    dim3 grid((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + 3) / 4), (unsigned)((nk + p.march - 1) / p.march));
+    if (grid.y > 65535 || grid.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the staged divergence / gradient");
+    int s;
+    if (is_divg) s = add_mode ? launch_divgrad_one<T, C, true, CURL3_DIVG>(p, grid, st) : launch_divgrad_one<T, C, false, CURL3_DIVG>(p, grid, st);
+    else s = add_mode ? launch_divgrad_one<T, C, true, CURL3_GRAD>(p, grid, st) : launch_divgrad_one<T, C, false, CURL3_GRAD>(p, grid, st);
+    if (s) return s;
+    return sgc_check_launch(is_divg ? "k_curl3p<DIVG>" : "k_curl3p<GRAD>");
+}
+
+template int sgc_launch_divgrad3<double, double>(const sgc_op *, bool, double *, const double *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
+template int sgc_launch_divgrad3<cplx, double>(const sgc_op *, bool, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
+template int sgc_launch_divgrad3<cplx, cplx>(const sgc_op *, bool, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
+
 template int sgc_launch_curl3<double, double>(const sgc_op *, double *, const double *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
 template int sgc_launch_curl3<cplx, double>(const sgc_op *, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
 template int sgc_launch_curl3<cplx, cplx>(const sgc_op *, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);

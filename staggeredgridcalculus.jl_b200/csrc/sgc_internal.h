@@ -150,6 +150,9 @@ struct OpBuilder {
 template <typename T, typename C>
 int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghost, bool add_mode,
                      int64_t k_begin, int64_t k_end, cudaStream_t st);
+template <typename T, typename C>
+int sgc_launch_divgrad3(const sgc_op *op, bool is_divg, T *G, const T *F, const void *const *ghost, bool add_mode,
+                        int64_t k_begin, int64_t k_end, cudaStream_t st);
 int sgc_check_common(int dtype, int ndim, const int64_t *N);
 #define fail sgc_fail
 #define check_launch sgc_check_launch

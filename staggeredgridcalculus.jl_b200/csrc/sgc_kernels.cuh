@@ -655,7 +655,13 @@ struct CurlCellBC {
     bool x_lo_zero, y_lo_zero;
 };
 
-template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, bool XSHFL>
+// MODE selects which of the staged data and of the six ∂ terms are used:
+//   CURL3_CURL  G = ∇×F                                   (slots 0,1,2 = Fx, Fy, Fz)
+//   CURL3_DIVG  g = ∂xF_x + ∂yF_y + ∂zF_z  (apply_divg!, divergence.jl:41-66): slot 0 = F_z (the z-differenced
+//               slot), slot 1 = F_x (x-differenced), slot 2 = F_y (y-differenced); one output, terms in x,y,z order
+//   CURL3_GRAD  G_w = ∂w f                  (apply_grad!, gradient.jl:41-59): slot 0 = f, differenced along all axes
+enum : int { CURL3_CURL = 0, CURL3_DIVG = 1, CURL3_GRAD = 2 };
+template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, bool XSHFL, int MODE = CURL3_CURL>
 __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__ CurlParams<T, C> p) {
     static_assert(TX % 32 == 0, "a warp must lie inside one row");
     static_assert(TX * TY >= 2 * TX + 2 * TY, "not enough threads for the halo copies");
@@ -711,7 +717,9 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             if (hj >= Ny) { hj = 0; ok = (p.bc_hi[1] == BC_BLOCH); }
             if (hj < 0) { hj = Ny - 1; ok = (p.bc_lo[1] == BC_BLOCH); }
             if (ok) {
-                hcomp = (lin < TX) ? 0 : 2;
+                hcomp = (lin < TX) ? 0 : 2;  // y-halo row of slot 0 and slot 2
+                if (MODE == CURL3_DIVG && hcomp == 0) hcomp = -1;  // divergence: only slot 2 (F_y) is y-differenced
+                if (MODE == CURL3_GRAD && hcomp == 2) hcomp = -1;  // gradient: only slot 0 (f)
                 hdst = (fy ? nvy : 0) * PITCH + (x + (fx ? 0 : 1));
                 hsrc = (int64_t)hj * sy + (i0 + x);
             }
@@ -725,7 +733,9 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             if (hi >= Nx) { hi = 0; ok = (p.bc_hi[0] == BC_BLOCH); }
             if (hi < 0) { hi = Nx - 1; ok = (p.bc_lo[0] == BC_BLOCH); }
             if (ok) {
-                hcomp = (q < TY) ? 1 : 2;
+                hcomp = (q < TY) ? 1 : 2;  // x-halo column of slot 1 and slot 2
+                if (MODE == CURL3_DIVG && hcomp == 2) hcomp = -1;  // divergence: only slot 1 (F_x) is x-differenced
+                if (MODE == CURL3_GRAD) hcomp = (q < TY) ? 0 : -1;  // gradient: the x-halo of slot 0 (f)
                 hdst = (y + (fy ? 0 : 1)) * PITCH + (fx ? nvx : 0);
                 hsrc = (int64_t)(j0 + y) * sy + hi;
             }
@@ -759,13 +769,13 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             if (kp >= 0 && kp < Nz) {
                 if (valid) {
                     cp_async_elem(st + self, p.F[0] + off_issue + ij);
-                    cp_async_elem(st + COMP + self, p.F[1] + off_issue + ij);
-                    if (centre) cp_async_elem(st + 2 * COMP + self, p.F[2] + off_issue + ij);
+                    if (MODE == CURL3_CURL || (MODE == CURL3_DIVG && centre)) cp_async_elem(st + COMP + self, p.F[1] + off_issue + ij);
+                    if (MODE != CURL3_GRAD && centre) cp_async_elem(st + 2 * COMP + self, p.F[2] + off_issue + ij);
                 }
                 if (centre && hcomp >= 0) cp_async_elem(hsm + stage_issue * STAGE, hbase + off_issue);
             } else if (valid) {  // plane outside the slab: wrap-around plane or the neighbour rank's plane
                 cp_async_elem(st + self, p.ghost[0] + ij);
-                cp_async_elem(st + COMP + self, p.ghost[1] + ij);
+                if (MODE == CURL3_CURL) cp_async_elem(st + COMP + self, p.ghost[1] + ij);
             }
         }
         cp_async_commit();
@@ -784,7 +794,8 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
         const int k = k0 + t;
         T g0 = Z, g1 = Z, g2 = Z;
         if (ADD && valid) {  // issue the read-modify-write loads early
-            g0 = ldg_plain(p.G[0] + off_out); g1 = ldg_plain(p.G[1] + off_out); g2 = ldg_plain(p.G[2] + off_out);
+            g0 = ldg_plain(p.G[0] + off_out);
+            if (MODE != CURL3_DIVG) { g1 = ldg_plain(p.G[1] + off_out); g2 = ldg_plain(p.G[2] + off_out); }
         }
         cp_async_wait<S - 3>();  // slots ≤ t+1 have landed (for this thread) ...
         __syncthreads();         // ... and for everybody; everybody has also finished plane t−1
@@ -798,40 +809,55 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
         if (t == 0) { xlo = slo[self]; ylo = slo[COMP + self]; }
         const T xhi = shi[self], yhi = shi[COMP + self];
         const T xc = fz ? xlo : xhi;
-        const T yc = fz ? ylo : yhi;
-        const T zc = sc[2 * COMP + self];
+        // slot 1 is staged on centre planes only for the divergence: read it there, not through the carry
+        const T yc = (MODE == CURL3_GRAD) ? Z : ((MODE == CURL3_DIVG) ? sc[COMP + self] : (fz ? ylo : yhi));
+        const T zc = (MODE == CURL3_GRAD) ? Z : sc[2 * COMP + self];
         const C czk = p.c[2][k];
         T gx, gy, gz;
 
         if (tile_plain && k > 0 && k < Nz - 1) {
             // ---- fast path: no boundary in reach; every term is c·(nb − cur) ------------------------
-            const T xn = sc[ynb], zn = sc[2 * COMP + ynb];
-            T yn, zx;
-            if (XSHFL) {
-                yn = fx ? shfl_down1(yc) : shfl_up1(yc);
-                zx = fx ? shfl_down1(zc) : shfl_up1(zc);
-                if (xedge) { yn = sc[COMP + xnb]; zx = sc[2 * COMP + xnb]; }
+            if (MODE == CURL3_CURL) {
+                const T xn = sc[ynb], zn = sc[2 * COMP + ynb];
+                T yn, zx;
+                if (XSHFL) {
+                    yn = fx ? shfl_down1(yc) : shfl_up1(yc);
+                    zx = fx ? shfl_down1(zc) : shfl_up1(zc);
+                    if (xedge) { yn = sc[COMP + xnb]; zx = sc[2 * COMP + xnb]; }
+                } else {
+                    yn = sc[COMP + xnb];
+                    zx = sc[2 * COMP + xnb];
+                }
+                const T dzx = mul(czk, sub(xhi, xlo));
+                const T dzy = mul(czk, sub(yhi, ylo));
+                const T dyx = mul(cys, sub(xn, xc));
+                const T dyz = mul(cys, sub(zn, zc));
+                const T dxy = mul(cxs, sub(yn, yc));
+                const T dxz = mul(cxs, sub(zx, zc));
+                if (ADD) {
+                    gx = add(add(g0, neg(dzy)), dyz);
+                    gy = add(add(g1, dzx), neg(dxz));
+                    gz = add(add(g2, neg(dyx)), dxy);
+                } else {
+                    gx = add(add(Z, neg(dzy)), dyz);
+                    gy = add(dzx, neg(dxz));
+                    gz = add(neg(dyx), dxy);
+                }
+            } else if (MODE == CURL3_DIVG) {
+                const T dz = mul(czk, sub(xhi, xlo));                 // ∂z of slot 0 (F_z)
+                const T dy = mul(cys, sub(sc[2 * COMP + ynb], zc));    // ∂y of slot 2 (F_y)
+                const T dx = mul(cxs, sub(sc[COMP + xnb], yc));        // ∂x of slot 1 (F_x)
+                gx = ADD ? add(add(add(g0, dx), dy), dz) : add(add(dx, dy), dz);  // divergence.jl:52-63: x, then y, then z
+                gy = Z; gz = Z;
             } else {
-                yn = sc[COMP + xnb];
-                zx = sc[2 * COMP + xnb];
-            }
-            const T dzx = mul(czk, sub(xhi, xlo));
-            const T dzy = mul(czk, sub(yhi, ylo));
-            const T dyx = mul(cys, sub(xn, xc));
-            const T dyz = mul(cys, sub(zn, zc));
-            const T dxy = mul(cxs, sub(yn, yc));
-            const T dxz = mul(cxs, sub(zx, zc));
-            if (ADD) {
-                gx = add(add(g0, neg(dzy)), dyz);
-                gy = add(add(g1, dzx), neg(dxz));
-                gz = add(add(g2, neg(dyx)), dxy);
-            } else {
-                gx = add(add(Z, neg(dzy)), dyz);
-                gy = add(dzx, neg(dxz));
-                gz = add(neg(dyx), dxy);
+                gx = mul(cxs, sub(sc[xnb], xc));   // ∂x f
+                gy = mul(cys, sub(sc[ynb], xc));   // ∂y f
+                gz = mul(czk, sub(xhi, xlo));      // ∂z f
+                if (ADD) { gx = add(g0, gx); gy = add(g1, gy); gz = add(g2, gz); }
             }
         } else {
             // ---- general path: boundary rules folded in (same code as k_curl3) -----------------------
+            // z term of slot 0 (and slot 1), y terms of slot 0 / slot 2, x terms of slot 1 / slot 2 (slot 0 for GRAD)
             T dzx, dzy;
             {
                 T xh = xhi, yh = yhi, xl = xlo, yl = ylo;
@@ -869,8 +895,10 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             }
             T dxy, dxz;
             {
-                T yn = sc[COMP + xnb], zn = sc[2 * COMP + xnb];
-                if (XSHFL) {
+                // first operand pair: slot 1 (slot 0 for the gradient); second: slot 2
+                const T c1v = (MODE == CURL3_GRAD) ? xc : yc;
+                T yn = (MODE == CURL3_GRAD) ? sc[xnb] : sc[COMP + xnb], zn = sc[2 * COMP + xnb];
+                if (XSHFL && MODE == CURL3_CURL) {
                     const T ys = fx ? shfl_down1(yc) : shfl_up1(yc);
                     const T zs = fx ? shfl_down1(zc) : shfl_up1(zc);
                     if (!xedge) { yn = ys; zn = zs; }
@@ -878,32 +906,42 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
                 T yh, yl, zh, zl;
                 bool zero_term = false;
                 if (fx) {
-                    yh = yn; zh = zn; yl = yc; zl = zc;
+                    yh = yn; zh = zn; yl = c1v; zl = zc;
                     if (xkind == 1) { yh = mul_e(p.e[0], yh, p.e_real[0]); zh = mul_e(p.e[0], zh, p.e_real[0]); }
                     else if (xkind == 2) { yh = Z; zh = Z; }
                     if (x_lo_zero) { yl = Z; zl = Z; }
                 } else {
-                    yh = yc; zh = zc; yl = yn; zl = zn;
+                    yh = c1v; zh = zc; yl = yn; zl = zn;
                     if (xkind == 1) { yl = div_e(yl, p.e[0], p.e_real[0]); zl = div_e(zl, p.e[0], p.e_real[0]); }
                     else if (xkind == 2) zero_term = true;
                 }
                 dxy = zero_term ? Z : mul(cxi, sub(yh, yl));
                 dxz = zero_term ? Z : mul(cxi, sub(zh, zl));
             }
-            if (ADD) {
-                gx = add(add(g0, neg(dzy)), dyz);
-                gy = add(add(g1, dzx), neg(dxz));
-                gz = add(add(g2, neg(dyx)), dxy);
+            if (MODE == CURL3_CURL) {
+                if (ADD) {
+                    gx = add(add(g0, neg(dzy)), dyz);
+                    gy = add(add(g1, dzx), neg(dxz));
+                    gz = add(add(g2, neg(dyx)), dxy);
+                } else {
+                    gx = add(add(Z, neg(dzy)), dyz);
+                    gy = add(dzx, neg(dxz));
+                    gz = add(neg(dyx), dxy);
+                }
+            } else if (MODE == CURL3_DIVG) {
+                gx = ADD ? add(add(add(g0, dxy), dyz), dzx) : add(add(dxy, dyz), dzx);
+                gy = Z; gz = Z;
             } else {
-                gx = add(add(Z, neg(dzy)), dyz);
-                gy = add(dzx, neg(dxz));
-                gz = add(neg(dyx), dxy);
+                gx = dxy; gy = dyx; gz = dzx;
+                if (ADD) { gx = add(g0, gx); gy = add(g1, gy); gz = add(g2, gz); }
             }
         }
         if (valid) {
             stg_stream(p.G[0] + off_out, gx);
-            stg_stream(p.G[1] + off_out, gy);
-            stg_stream(p.G[2] + off_out, gz);
+            if (MODE != CURL3_DIVG) {
+                stg_stream(p.G[1] + off_out, gy);
+                stg_stream(p.G[2] + off_out, gz);
+            }
         }
         xlo = xhi;
         ylo = yhi;

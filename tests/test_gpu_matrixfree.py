@@ -381,6 +381,11 @@ def test_fused_compositions_match_oracle_and_sweeps(S, N, cplx_field, cplx_coef)
                     what = f"{name} N={N} fwd={isfwd} bloch={isbloch} {op}"
                     assert_parity(Ga.numpy(), Gref, what + " (fused vs oracle)", exact=True)
                     assert_parity(Ga.numpy(), Gb.numpy(), what + " (fused vs sweeps)", exact=True)
+                    if K == 3:  # the 3-D forms default to the staged z-march; variant 6 = the row-register kernel
+                        Gc = dev(S, G0)
+                        o.set_tuning(0, 0, 0, 6)
+                        o.apply(Gc, dev(S, F), op)
+                        assert_parity(Gc.numpy(), Gref, what + " (row-register kernel vs oracle)", exact=True)
                 o.destroy()
     assert fused_seen > 0, "the one-launch path never ran"
 
