@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--graph", default="off", choices=["on", "off"])
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
+    ap.add_argument("--sync", default="barrier", choices=["flags", "barrier"],
+                    help="peer-memory halos: neighbour flags inside the stencil kernel, or a barrier kernel before every apply")
     ap.add_argument("--slab", default="256,256,256", help="per-GPU slab Nx,Ny,Nz (default: BASELINE configs[1]; 1024,1024,128 = configs[4] at 8 GPUs)")
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="side experiments only: skip the host-array leg")
@@ -234,8 +236,11 @@ def main():
             sys.stderr.write(f"[bench] symmetric memory unavailable ({type(ex).__name__}: {str(ex)[:120]}); using NCCL halos\n")
     if world > 1 and arena is None:
         halo = "NCCL send/recv on a side stream, overlapped with the interior planes"
-    c_dual = SlabCurl(S.SGC_C128, NLOCAL, [True] * 3, [ddual[0], ddual[1], ddual[2][k0:k1]], bl, e, rank, world, arena=arena)
-    c_prim = SlabCurl(S.SGC_C128, NLOCAL, [False] * 3, [dprim[0], dprim[1], dprim[2][k0:k1]], bl, e, rank, world, arena=arena)
+    sync = args.sync if arena is not None else "barrier"
+    if arena is not None and sync == "flags":
+        halo += "; neighbour synchronisation inside the kernel (flags over NVLink), no barrier kernel"
+    c_dual = SlabCurl(S.SGC_C128, NLOCAL, [True] * 3, [ddual[0], ddual[1], ddual[2][k0:k1]], bl, e, rank, world, arena=arena, sync=sync)
+    c_prim = SlabCurl(S.SGC_C128, NLOCAL, [False] * 3, [dprim[0], dprim[1], dprim[2][k0:k1]], bl, e, rank, world, arena=arena, sync=sync)
 
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     def rnd():
@@ -313,6 +318,7 @@ def main():
     nbytes = 3 * M * 16
     e2e_val, e2e_s, e2e_steps, e2e_mode = None, 0.0, 1, "skipped (--no-e2e)"
     if not args.no_e2e:
+        c_dual.sync = c_prim.sync = "barrier"  # host copies touch the fields between applies: full barriers
         E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
         E_host.copy_(E.t)
         Out_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()

@@ -174,6 +174,21 @@ int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int ndim, cons
                    int coef_complex, const int *isbloch, const double *e, const double *alpha,
                    void *stream);
 
+/* Neighbour synchronisation folded into the fused 3-D curl kernel (z-slabs in peer-mapped memory):
+ * instead of a barrier kernel before every apply, the CTAs that touch the first (last) plane of
+ * the slab wait (acquire loads) until the lower (upper) neighbour has published `epoch - 1`, and
+ * per side the last boundary CTA to finish publishes `epoch` into that neighbour's memory
+ * (release store over NVLink) — interior CTAs neither wait nor take part.  wait_lo / wait_hi: DEVICE pointers (this rank's memory) to the
+ * Int64 flags the lower / upper neighbour writes (NULL: no neighbour on that side); post_lo /
+ * post_hi: PEER pointers to the matching flags in the neighbours' memory; counter: two device uint32
+ * (lower / upper side tickets), zero-initialised, shared by the operators of a rank.  All ranks must issue the same sequence of
+ * synchronised applies with epoch = 1, 2, 3, ...; flags start at 0 and the inputs of the first
+ * apply must be complete on all ranks (one ordinary barrier). */
+int sgc_op_set_peer_sync(sgc_op *op, const void *wait_lo, const void *wait_hi, void *post_lo, void *post_hi,
+                         void *counter);
+int sgc_op_apply_synced(const sgc_op *op, void *G, const void *F, int opmode, const void *const *ghost,
+                        int64_t epoch, void *stream);
+
 /* Fused curl-of-curl  G OP C2(C1 F)  in one pass over memory: the intermediate field
  * H = C1 F stays in shared memory (96 instead of 192 bytes per ComplexF64 cell).  Bit-identical
  * to sgc_op_apply(c1, H, F, SET) followed by sgc_op_apply(c2, G, H, opmode); replaces the pair

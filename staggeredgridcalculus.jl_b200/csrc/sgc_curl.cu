@@ -41,6 +41,13 @@ int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghos
     }
     p.Nx = (int)op->N[0]; p.Ny = (int)op->N[1]; p.Nz = (int)op->N[2];
     p.k_begin = (int)k_begin; p.k_end = (int)k_end;
+    if (op->sync_epoch > 0) {
+        if ((op->variant & 0xF) != 0 || k_begin != 0 || k_end != op->N[2] || !op->sync_counter)
+            return sgc_fail(SGC_ERR_INVALID, "synchronised apply needs the default kernel, the whole slab and sgc_op_set_peer_sync");
+        for (int sd = 0; sd < 2; ++sd) { p.sync_wait[sd] = op->sync_wait[sd]; p.sync_post[sd] = op->sync_post[sd]; }
+        p.sync_epoch = op->sync_epoch;
+        p.sync_counter = op->sync_counter;
+    }
 
     const int kernel_variant = op->variant & 0xF;
     // defaults from the 256^3 sweeps on B200 (profiles/r1_sweep_curl_256*.jsonl): 32x4 tiles, 6-stage

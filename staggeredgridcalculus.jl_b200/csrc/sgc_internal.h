@@ -120,6 +120,11 @@ struct sgc_op {
     size_t fused_off[3] = {0, 0, 0};
     int fused_pat = -1;           // PAT_* when the term list is one of the one-launch compositions
     int lo_iface = 0, hi_iface = 0;
+    // neighbour synchronisation folded into the fused curl kernel (sgc_op_set_peer_sync)
+    const long long *sync_wait[2] = {nullptr, nullptr};
+    long long *sync_post[2] = {nullptr, nullptr};
+    unsigned *sync_counter = nullptr;
+    mutable long long sync_epoch = 0;                // epoch of the apply being launched (0: plain apply)
     HV alpha = {1.0, 0.0, false};                    // α of a curl operator (for the ghost-plane coefficients)
     sgc::cplx cz_ghost[2] = {{1.0, 0.0}, {1.0, 0.0}};  // α·∆z⁻¹ of the planes −1 / Nz (slab neighbours)
     int tile_x = 0, tile_y = 0, march = 0, variant = 0;

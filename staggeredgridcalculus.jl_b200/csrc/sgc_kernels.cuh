@@ -379,7 +379,25 @@ struct CurlParams {
     int Nx, Ny, Nz;
     int k_begin, k_end;  // planes to produce
     int march;           // planes per CTA
+    // neighbour synchronisation folded into the kernel (z-slabs in peer memory, no barrier kernel):
+    // the CTAs that touch the first (last) plane of the slab wait until the lower (upper) neighbour's
+    // boundary CTAs of its previous apply are done (flag the neighbour wrote into MY memory ≥ epoch − 1);
+    // per side, the last boundary CTA to finish publishes `epoch` into that neighbour's memory.
+    // Interior CTAs neither wait nor count.  sync_counter: two tickets (lower, upper).  epoch == 0: off.
+    const long long *sync_wait[2];
+    long long *sync_post[2];
+    long long sync_epoch;
+    unsigned *sync_counter;
 };
+
+SGC_D long long ld_acquire_sys(const long long *p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SGC_D void st_release_sys(long long *p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // One CTA owns a TX×TY column of cells and marches `march` planes up in z.
 //   * Fx, Fy: two planes live in registers (`lo`, `hi`); ∂z = cz[k]·(hi − lo) for both forward
@@ -757,6 +775,18 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
     const int base = fz ? k0 : k0 - 1;  // grid plane of slot 0
     const T Z = zero_of(T{});
 
+    if (p.sync_epoch > 0 && (k0 == 0 || k1 == Nz)) {
+        // this CTA reads a neighbour's plane or overwrites a plane a neighbour may still be reading: the
+        // neighbour on that side must have finished the boundary CTAs of its previous apply
+        if (lin == 0) {
+            if (k0 == 0 && p.sync_wait[0])
+                while (ld_acquire_sys(p.sync_wait[0]) < p.sync_epoch - 1) __nanosleep(64);
+            if (k1 == Nz && p.sync_wait[1])
+                while (ld_acquire_sys(p.sync_wait[1]) < p.sync_epoch - 1) __nanosleep(64);
+        }
+        __syncthreads();
+    }
+
     // running state of the producer side: slot index, its ring stage, its grid plane offset
     int jj_issue = 0;
     int stage_issue = 0;
@@ -947,6 +977,25 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
         ylo = yhi;
     }
     cp_async_wait<0>();
+    if (p.sync_epoch > 0 && (k0 == 0 || k1 == Nz)) {
+        // per side: the last boundary CTA to finish tells that neighbour that this rank's apply #epoch has
+        // written (and no longer reads) the planes at that interface; interior CTAs take no part
+        __syncthreads();
+        if (lin == 0) {
+            __threadfence();
+            const unsigned side_total = gridDim.x * gridDim.y;
+            if (k0 == 0 && p.sync_post[0] && atomicAdd(p.sync_counter, 1u) == side_total - 1) {
+                p.sync_counter[0] = 0;
+                __threadfence_system();
+                st_release_sys(p.sync_post[0], p.sync_epoch);
+            }
+            if (k1 == Nz && p.sync_post[1] && atomicAdd(p.sync_counter + 1, 1u) == side_total - 1) {
+                p.sync_counter[1] = 0;
+                __threadfence_system();
+                st_release_sys(p.sync_post[1], p.sync_epoch);
+            }
+        }
+    }
 }
 
 }  // namespace sgc

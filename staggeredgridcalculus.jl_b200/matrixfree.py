@@ -151,6 +151,20 @@ class Operator:
         check(lib.sgc_op_apply_range(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr,
                                      int(k_begin), int(k_end), stream_handle(stream)))
 
+    def set_peer_sync(self, wait_lo, wait_hi, post_lo, post_hi, counter):
+        """Device / peer pointers (ints or None) of the neighbour flags, see `sgc_op_set_peer_sync`."""
+        v = lambda x: None if x is None else C.c_void_p(int(x))
+        check(lib.sgc_op_set_peer_sync(self._h, v(wait_lo), v(wait_hi), v(post_lo), v(post_hi), v(counter)))
+
+    def apply_synced(self, G, F, op, ghost, epoch, stream=None):
+        """One whole-slab apply whose neighbour synchronisation happens inside the kernel."""
+        self._check_arrays(G, F)
+        garr = None
+        if ghost is not None:
+            garr = (C.c_void_p * self.n_in)(*[None if g is None else int(g) for g in ghost])
+        check(lib.sgc_op_apply_synced(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr, int(epoch),
+                                      stream_handle(stream)))
+
     def apply_after(self, first: "Operator", G: DeviceArray, F: DeviceArray, op="=", k_begin=None, k_end=None,
                     ghost_lo=None, ghost_hi=None, stream=None):
         """Fused curl-of-curl `G OP self(first(F))` in one pass over memory (the intermediate field

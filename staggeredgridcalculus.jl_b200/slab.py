@@ -118,6 +118,11 @@ class PeerArena:
         self.hdl = symm.rendezvous(self.buf, group.group_name)
         self.base = self.buf.data_ptr()
         self.used = 0
+        # neighbour flags for the in-kernel synchronisation: [0] written by the lower neighbour, [1] by the upper
+        # one, [2] the CTA ticket counter of this rank; `epoch` counts this rank's synchronised applies
+        self.flags = self.array((4,), np.float64)
+        self.flags.t.zero_()
+        self.epoch = 0
 
     def array(self, shape, dtype=np.complex128) -> DeviceArray:
         n = int(np.prod(shape, dtype=np.int64))
@@ -149,8 +154,14 @@ class SlabCurl:
     (every rank's `F` must then be the same carve-out of the arena, and slabs of equal size)."""
 
     def __init__(self, dtype_code, N, isfwd, dlinv, isbloch, e, rank, world, alpha=1.0, backend_cls=CudaBackend,
-                 group=None, arena: "PeerArena | None" = None):
+                 group=None, arena: "PeerArena | None" = None, sync="barrier"):
+        """`sync` (peer-memory transport only): "barrier" = a device-side barrier of all ranks before every apply
+        (safe with anything else touching the fields in between); "flags" = neighbour synchronisation inside the
+        stencil kernel (all ranks must then run the same sequence of applies on the arena's fields and nothing
+        else may modify those fields in between)."""
         self.rank, self.world, self.group = rank, world, group
+        self.sync = sync
+        self.bloch_z = bool(isbloch[2])
         self.N = tuple(int(n) for n in N)
         self.plan = halo_plan(rank, world, bool(isfwd[2]), bool(isbloch[2]))
         self.backend = backend_cls(dtype_code, self.N, isfwd, dlinv, isbloch, e, alpha, self.plan["lo_interface"],
@@ -161,17 +172,40 @@ class SlabCurl:
         if self.arena is None and self.plan["recv_from"] is not None:
             self.ghost = self.backend.alloc_ghost()
 
+    def _setup_flag_sync(self):
+        """Neighbour ranks along z (ring if the global z boundary is Bloch) and their flag addresses."""
+        a, r, w = self.arena, self.rank, self.world
+        lo = r - 1 if r > 0 else (w - 1 if self.bloch_z and w > 1 else None)
+        hi = r + 1 if r < w - 1 else (0 if self.bloch_z and w > 1 else None)
+        f = a.flags
+        wait_lo = f.ptr if lo is not None else None           # flags[0]: written by my lower neighbour
+        wait_hi = f.ptr + 8 if hi is not None else None       # flags[1]: written by my upper neighbour
+        post_lo = a.peer_ptr(f, lo) + 8 if lo is not None else None   # I am the UPPER neighbour of `lo`
+        post_hi = a.peer_ptr(f, hi) if hi is not None else None       # I am the LOWER neighbour of `hi`
+        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16)
+        self._flag_sync_ready = True
+
     def _apply_peer(self, G, F, op):
         """One fused kernel; the ghost pointers are the neighbour's planes (NVLink loads)."""
         Nz, plan = self.N[2], self.plan
         plane = self.N[0] * self.N[1]
         M = plane * Nz
-        self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
         ghost = None
         if plan["recv_from"] is not None:
             base = self.arena.peer_ptr(F, plan["recv_from"])
             kpl = 0 if plan["boundary"] == "top" else Nz - 1
             ghost = [base + (c * M + kpl * plane) * self.esize for c in range(2)] + [None]
+        if self.sync == "flags":
+            # neighbour synchronisation inside the kernel: boundary CTAs wait for the neighbours' previous apply,
+            # the last CTA publishes this one — no barrier kernel, the interior never waits
+            if not getattr(self, "_flag_sync_ready", False):
+                self._setup_flag_sync()
+            if self.arena.epoch == 0:
+                self.arena.barrier()  # the inputs of the very first synchronised apply
+            self.arena.epoch += 1
+            self.backend.op.apply_synced(G, F, op, ghost, self.arena.epoch)
+            return
+        self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
         self.backend.op.apply_range(G, F, op, 0, Nz, ghost)
 
     def apply(self, G, F, op="="):

@@ -79,3 +79,66 @@ def test_slab_curl_matches_single_gpu(use_arena):
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), results, use_arena), nprocs=world, join=True)
     assert all(results.get(r) is True for r in range(world)), dict(results)
+
+
+def _worker_flags(rank, world, port, results):
+    """A chain of alternating forward / backward curls (E → H → E → …, ping-pong between two arena fields) with the
+    neighbour synchronisation inside the kernel (`sync="flags"`): every rank's slab of the final field must equal
+    the single-GPU chain bit for bit — which fails if a halo is read before it is complete (RAW) or a plane is
+    overwritten while a neighbour still reads it (WAR)."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sgc_b200 as S
+        from sgc_b200.slab import SlabCurl, PeerArena, partition_planes
+        rng = np.random.default_rng(6)
+        N = (64, 40, 6 * world)
+        E0 = np.asfortranarray(rng.uniform(-1, 1, N + (3,)) + 1j * rng.uniform(-1, 1, N + (3,)))
+        d1 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+        d2 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+        e = [np.exp(-0.3j), np.exp(0.5j), np.exp(-0.9j)]
+        k0, k1 = partition_planes(N[2], world)[rank]
+        Nl = (N[0], N[1], k1 - k0)
+        ok = True
+        arena = PeerArena(2 * 3 * N[0] * N[1] * (k1 - k0) * 16 + 1024)
+        A, B = arena.array(Nl + (3,)), arena.array(Nl + (3,))
+        iters = 6
+        for bz in (True, False):
+            isbloch = [True, False, bz]
+            w1 = S.Operator.curl(S.SGC_C128, N, [True] * 3, d1, isbloch, e, alpha=0.25)
+            w2 = S.Operator.curl(S.SGC_C128, N, [False] * 3, d2, isbloch, e, alpha=0.25)
+            Ew, Hw = S.DeviceArray.from_numpy(E0), S.DeviceArray.zeros(N + (3,))
+            for _ in range(iters):
+                w1.apply(Hw, Ew, "=")
+                w2.apply(Ew, Hw, "=")
+            ref = Ew.numpy()[:, :, k0:k1, :]
+            c1 = SlabCurl(S.SGC_C128, Nl, [True] * 3, [d1[0], d1[1], d1[2][k0:k1]], isbloch, e, rank, world, alpha=0.25,
+                          arena=arena, sync="flags")
+            c2 = SlabCurl(S.SGC_C128, Nl, [False] * 3, [d2[0], d2[1], d2[2][k0:k1]], isbloch, e, rank, world, alpha=0.25,
+                          arena=arena, sync="flags")
+            arena.barrier()  # nobody still reads A / B of the previous case
+            A.t.copy_(S.DeviceArray.from_numpy(np.asfortranarray(E0[:, :, k0:k1, :])).t)
+            B.t.zero_()
+            arena.barrier()  # inputs complete everywhere before the flag-synchronised chain starts
+            for _ in range(iters):
+                c1.apply(B, A, "=")
+                c2.apply(A, B, "=")
+            torch.cuda.synchronize()
+            ok = ok and np.array_equal(A.numpy(), ref)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_flag_sync_chain_matches_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_flags, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert all(results.get(r) is True for r in range(world)), dict(results)
