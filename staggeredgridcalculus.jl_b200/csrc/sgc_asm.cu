@@ -340,6 +340,8 @@ static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
     }
     p.cols_per_group = a->cmpfirst ? a->Kin : 1;
     p.ngroups = a->cmpfirst ? a->M : (int64_t)a->Kin * a->M;
+    for (int nu = 0; nu < 3; ++nu)
+        for (int ax = 0; ax < 3; ++ax) p.cnt_tab[nu][ax] = a->count_tables + a->count_off[nu][ax];
     p.skip_enabled = 0;
     if (a->cmpfirst && !(a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M)) {
         const int64_t span = a->M / a->N[a->ndim - 1];  // cells per hyper-plane of the slowest axis = longest reach

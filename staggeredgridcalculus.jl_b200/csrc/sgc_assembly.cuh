@@ -56,6 +56,7 @@ struct AsmParams {
     // hold entries; CTAs entirely outside [near_lo, near_hi) and the wrap planes skip the entry work
     int skip_enabled;
     int64_t near_lo, near_hi, wrap_span;
+    const int *cnt_tab[3][3];     // [nu][axis] → int[N_axis]: separable per-column counts (valid when all rows are kept)
     int prefix_enabled;
     const int64_t *prefix[4][3];  // [set][axis] → int64[N_axis + 1], exclusive prefix sums
     int64_t set_base[4];          // entries before the first group of the set
@@ -200,10 +201,13 @@ SGC_D void sort_entries(R (&rows)[E], T (&vals)[E]) {
     }
 }
 
-// sorted entries of column (nu, c) in registers; returns the count.  R is the row type: 32-bit
+// Entries of column (nu, c) in registers, UNSORTED, plus the rank each one takes in ascending row
+// order (invalid slots carry the largest row and rank last); returns the count.  Ranking by counting
+// (E(E−1)/2 comparisons) instead of a sorting network keeps the values — up to 4 registers each — in
+// place: they are stored straight to their sorted shared-memory slot.  R is the row type: 32-bit
 // when the matrix has fewer than 2^31 rows (half the register and ALU cost), else 64-bit.
 template <typename T, typename IDX, typename R, int E>
-SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3], R (&rows)[E], T (&vals)[E]) {
+SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[3], R (&rows)[E], T (&vals)[E], int (&rank)[E]) {
     const R INVALID = (R)(sizeof(R) == 4 ? 0x7fffffff : 0x7fffffffffffffffLL);
 #pragma unroll
     for (int q = 0; q < E; ++q) { rows[q] = INVALID; vals[q] = zero_of(T{}); }
@@ -220,7 +224,20 @@ SGC_D int column_entries_of(const AsmParams<T> &p, int nu, IDX c, const IDX sub[
             if (ok[1]) { rows[2 * q + 1] = r[1]; vals[2 * q + 1] = v[1]; }
         }
     }
-    sort_entries<E>(rows, vals);
+    if (sizeof(T) > 8) {  // wide values: rank, do not move them
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int rk = 0;
+#pragma unroll
+            for (int f = 0; f < E; ++f)
+                if (f != e) rk += (rows[f] < rows[e] || (rows[f] == rows[e] && f < e)) ? 1 : 0;
+            rank[e] = rk;
+        }
+    } else {              // 8-byte values: the sorting network is cheaper (measured), slots are then compile-time
+        sort_entries<E>(rows, vals);
+#pragma unroll
+        for (int e = 0; e < E; ++e) rank[e] = e;
+    }
     return cnt;
 }
 
@@ -285,16 +302,28 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
     IDX c = 0, sub[3] = {0, 0, 0};
     if (live) group_decode<T, IDX>(p, g, nu0, c, sub);
 
+    // 8-byte values: all entries of the group are produced once, up front, sorted by the network and held in
+    // registers across the scan (fewest instructions; the kernel is issue-bound).  Wider values: per-column counts
+    // first (from the separable tables when all rows are kept) and the entries one column at a time when they are
+    // staged, ranked instead of moved — 56 instead of 96 registers for ComplexF64.
+    constexpr bool LATE = sizeof(T) > 8;
+    constexpr bool HOLD = WRITES && !LATE;
     int cnt[NCOLS];
-    R rows[WRITES ? NCOLS : 1][E];
-    T vals[WRITES ? NCOLS : 1][E];
+    R hrows[HOLD ? NCOLS : 1][E];
+    T hvals[HOLD ? NCOLS : 1][E];
     int mine = 0;
 #pragma unroll
     for (int q = 0; q < NCOLS; ++q) {
         cnt[q] = 0;
         if (live) {
-            if (WRITES) cnt[q] = column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows[WRITES ? q : 0], vals[WRITES ? q : 0]);
-            else cnt[q] = column_count_of<T, IDX, R>(p, nu0 + q, c, sub);
+            if (HOLD) {
+                int rk[E];
+                cnt[q] = column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, hrows[HOLD ? q : 0], hvals[HOLD ? q : 0], rk);
+            } else if (p.prefix_enabled) {
+                cnt[q] = p.cnt_tab[nu0 + q][0][sub[0]] + p.cnt_tab[nu0 + q][1][sub[1]] + p.cnt_tab[nu0 + q][2][sub[2]];
+            } else {
+                cnt[q] = column_count_of<T, IDX, R>(p, nu0 + q, c, sub);
+            }
         }
         mine += cnt[q];
     }
@@ -331,12 +360,26 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)SLOTS);
             const int s0 = threadIdx.x * (PADK + 1);
 #pragma unroll
-            for (int q = 0; q < NCOLS; ++q)
+            for (int q = 0; q < NCOLS; ++q) {
+                if (HOLD) {
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    s_rows[s0 + q * E + e] = rows[WRITES ? q : 0][e];
-                    s_vals[s0 + q * E + e] = vals[WRITES ? q : 0][e];
+                    for (int e = 0; e < E; ++e) {
+                        s_rows[s0 + q * E + e] = hrows[HOLD ? q : 0][e];
+                        s_vals[s0 + q * E + e] = hvals[HOLD ? q : 0][e];
+                    }
+                } else {
+                    R rows[E];
+                    T vals[E];
+                    int rank[E];
+                    column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows, vals, rank);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {  // entry e goes to its rank within the column
+                        const int slot = s0 + q * E + rank[e];
+                        s_rows[slot] = rows[e];
+                        s_vals[slot] = vals[e];
+                    }
                 }
+            }
             __syncthreads();
             int64_t *rv = rowval + base + threadIdx.x;
             T *nz = nzval + base + threadIdx.x;
@@ -373,13 +416,28 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             int o = off0;
 #pragma unroll
             for (int q = 0; q < NCOLS; ++q) {
+                if (HOLD) {
 #pragma unroll
-                for (int e = 0; e < E; ++e)
-                    if (e < cnt[q]) {
-                        const int slot = (o + e) + (o + e) / PADK;
-                        s_rows[slot] = rows[WRITES ? q : 0][e];
-                        s_vals[slot] = vals[WRITES ? q : 0][e];
-                    }
+                    for (int e = 0; e < E; ++e)
+                        if (e < cnt[q]) {
+                            const int slot = (o + e) + (o + e) / PADK;
+                            s_rows[slot] = hrows[HOLD ? q : 0][e];
+                            s_vals[slot] = hvals[HOLD ? q : 0][e];
+                        }
+                } else {
+                    R rows[E];
+                    T vals[E];
+                    int rank[E];
+                    column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows, vals, rank);
+#pragma unroll
+                    for (int e = 0; e < E; ++e)
+                        if (rank[e] < cnt[q]) {  // valid entries rank before the invalid ones
+                            const int at = o + rank[e];
+                            const int slot = at + at / PADK;
+                            s_rows[slot] = rows[e];
+                            s_vals[slot] = vals[e];
+                        }
+                }
                 o += cnt[q];
             }
         }
