@@ -41,6 +41,23 @@ class DeviceCSC:
         cp, rv, nz = self.to_host()
         return sp.csc_matrix((nz, rv - self.index_base, cp - self.index_base), shape=(self.m, self.n))
 
+    def to_pinned_host(self):
+        """colptr / rowval / nzval copied into page-locked host tensors (what a Julia caller wraps as
+        `SparseMatrixCSC(m, n, colptr, rowval, nzval)` without a further copy)."""
+        outs = []
+        for t in (self.colptr, self.rowval, self.nzval):
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            outs.append(h)
+        torch.cuda.current_stream().synchronize()
+        return tuple(outs)
+
+    def save_npz(self, path):
+        """On-disk CSC dump for cross-language parity checks (numpy `.npz`: m, n, index_base, colptr, rowval,
+        nzval — Julia reads it with NPZ.jl, scipy with `load_npz_csc`)."""
+        cp, rv, nz = self.to_host()
+        np.savez(path, m=self.m, n=self.n, index_base=self.index_base, colptr=cp, rowval=rv, nzval=nz)
+
     def matvec(self, x: torch.Tensor) -> torch.Tensor:
         """`A * x` on the device (test utility; the reference's cross-check `mul!(g, A, f)`)."""
         code = _lib.SGC_C128 if self.nzval.dtype == torch.complex128 else _lib.SGC_F64
@@ -50,6 +67,14 @@ class DeviceCSC:
                                  C.c_void_p(self.nzval.data_ptr()), self.index_base, code, C.c_void_p(x.data_ptr()),
                                  C.c_void_p(y.data_ptr()), stream_handle()))
         return y
+
+
+def load_npz_csc(path):
+    """Inverse of `DeviceCSC.save_npz` on the host: a scipy `csc_matrix`."""
+    import scipy.sparse as sp
+    d = np.load(path)
+    b = int(d["index_base"])
+    return sp.csc_matrix((d["nzval"], d["rowval"] - b, d["colptr"] - b), shape=(int(d["m"]), int(d["n"])))
 
 
 class _Asm:

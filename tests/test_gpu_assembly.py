@@ -198,6 +198,24 @@ def test_row_partition_on_a_tall_grid_skips_far_columns(S):
                 assert np.array_equal(stacked.data, full.data), what
 
 
+def test_csc_hand_off_formats(S, tmp_path):
+    """pinned host arrays for the `SparseMatrixCSC(m,n,colptr,rowval,nzval)` constructor and the
+    on-disk `.npz` dump, both equal to the oracle's matrix."""
+    from sgc_b200.matrix import load_npz_csc
+    rng = np.random.default_rng(17)
+    N = (5, 4, 3)
+    dlinv = [rand_coef(rng, n, True) for n in N]
+    e = [np.exp(-0.1j), 1.0, np.exp(0.3j)]
+    A = S.create_curl([True, False, True], dlinv, [True, False, True], e)
+    R = O.create_curl([True, False, True], dlinv, [True, False, True], e)
+    cp, rv, nz = A.to_pinned_host()
+    assert cp.is_pinned() and rv.is_pinned() and nz.is_pinned()
+    assert np.array_equal(cp.numpy(), R.colptr) and np.array_equal(rv.numpy(), R.rowval) and np.array_equal(nz.numpy(), R.nzval)
+    A.save_npz(tmp_path / "curl.npz")
+    B = load_npz_csc(tmp_path / "curl.npz")
+    assert np.array_equal(B.indptr, R.colptr - 1) and np.array_equal(B.indices, R.rowval - 1) and np.array_equal(B.data, R.nzval)
+
+
 def test_matrix_times_field_equals_matrix_free(S):
     """test/curl.jl:54-57: `mul!(g, Curl, f)` ≈ `apply_curl!` (block ordering), on the device."""
     import torch
