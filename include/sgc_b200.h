@@ -183,9 +183,11 @@ int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int ndim, cons
  * post_hi: PEER pointers to the matching flags in the neighbours' memory; counter: two device uint32
  * (lower / upper side tickets), zero-initialised, shared by the operators of a rank.  All ranks must issue the same sequence of
  * synchronised applies with epoch = 1, 2, 3, ...; flags start at 0 and the inputs of the first
- * apply must be complete on all ranks (one ordinary barrier). */
+ * apply must be complete on all ranks (one ordinary barrier).  z_reverse: walk the z-chunks
+ * top-down; neighbouring ranks should alternate (rank parity), so that the chunks a rank runs
+ * FIRST face the chunks its neighbour ran first in the previous apply and never wait. */
 int sgc_op_set_peer_sync(sgc_op *op, const void *wait_lo, const void *wait_hi, void *post_lo, void *post_hi,
-                         void *counter);
+                         void *counter, int z_reverse);
 int sgc_op_apply_synced(const sgc_op *op, void *G, const void *F, int opmode, const void *const *ghost,
                         int64_t epoch, void *stream);
 

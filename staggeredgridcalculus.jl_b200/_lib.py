@@ -83,7 +83,7 @@ _PROTOS = {
                                  intp, dblp, dblp, C.c_void_p]),
     "sgc_apply_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, i64p, intp, vpp, vpp,
                                  C.c_int, intp, dblp, dblp, C.c_void_p]),
-    "sgc_op_set_peer_sync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgc_op_set_peer_sync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "sgc_op_apply_synced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, C.c_int64, C.c_void_p]),
     "sgc_op_apply_curlcurl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sgc_op_apply_curlcurl_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, vpp,

@@ -47,6 +47,7 @@ int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghos
         for (int sd = 0; sd < 2; ++sd) { p.sync_wait[sd] = op->sync_wait[sd]; p.sync_post[sd] = op->sync_post[sd]; }
         p.sync_epoch = op->sync_epoch;
         p.sync_counter = op->sync_counter;
+        p.z_reverse = op->sync_z_reverse;
     }
 
     const int kernel_variant = op->variant & 0xF;

@@ -124,6 +124,7 @@ struct sgc_op {
     const long long *sync_wait[2] = {nullptr, nullptr};
     long long *sync_post[2] = {nullptr, nullptr};
     unsigned *sync_counter = nullptr;
+    int sync_z_reverse = 0;
     mutable long long sync_epoch = 0;                // epoch of the apply being launched (0: plain apply)
     HV alpha = {1.0, 0.0, false};                    // α of a curl operator (for the ghost-plane coefficients)
     sgc::cplx cz_ghost[2] = {{1.0, 0.0}, {1.0, 0.0}};  // α·∆z⁻¹ of the planes −1 / Nz (slab neighbours)

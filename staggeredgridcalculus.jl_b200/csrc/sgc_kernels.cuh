@@ -388,6 +388,8 @@ struct CurlParams {
     long long *sync_post[2];
     long long sync_epoch;
     unsigned *sync_counter;
+    int z_reverse;  // walk the z-chunks top-down (ranks alternate, so that a rank's first wave never waits on the
+                    // chunks its neighbour runs last)
 };
 
 SGC_D long long ld_acquire_sys(const long long *p) {
@@ -768,7 +770,8 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
     const C cxs = fx ? cxi : neg(cxi);
     const C cys = fy ? cyj : neg(cyj);
 
-    const int k0 = p.k_begin + blockIdx.z * p.march;
+    const int zchunk = p.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    const int k0 = p.k_begin + zchunk * p.march;
     const int k1 = min(k0 + p.march, p.k_end);
     if (k0 >= k1) return;
     const int n = k1 - k0;              // planes to produce

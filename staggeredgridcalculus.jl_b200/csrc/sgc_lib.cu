@@ -686,13 +686,14 @@ extern "C" int sgc_op_apply_range(const sgc_op *op, void *G, const void *F, int 
 }
 
 extern "C" int sgc_op_set_peer_sync(sgc_op *op, const void *wait_lo, const void *wait_hi, void *post_lo, void *post_hi,
-                                    void *counter) {
+                                    void *counter, int z_reverse) {
     REQUIRE(op, "op is NULL");
     REQUIRE(op->fused_curl, "peer synchronisation is built into the fused 3-D curl kernel only");
     REQUIRE(counter, "counter is NULL");
     op->sync_wait[0] = (const long long *)wait_lo; op->sync_wait[1] = (const long long *)wait_hi;
     op->sync_post[0] = (long long *)post_lo; op->sync_post[1] = (long long *)post_hi;
     op->sync_counter = (unsigned *)counter;
+    op->sync_z_reverse = z_reverse ? 1 : 0;
     return SGC_OK;
 }
 

@@ -151,10 +151,10 @@ class Operator:
         check(lib.sgc_op_apply_range(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr,
                                      int(k_begin), int(k_end), stream_handle(stream)))
 
-    def set_peer_sync(self, wait_lo, wait_hi, post_lo, post_hi, counter):
+    def set_peer_sync(self, wait_lo, wait_hi, post_lo, post_hi, counter, z_reverse=False):
         """Device / peer pointers (ints or None) of the neighbour flags, see `sgc_op_set_peer_sync`."""
         v = lambda x: None if x is None else C.c_void_p(int(x))
-        check(lib.sgc_op_set_peer_sync(self._h, v(wait_lo), v(wait_hi), v(post_lo), v(post_hi), v(counter)))
+        check(lib.sgc_op_set_peer_sync(self._h, v(wait_lo), v(wait_hi), v(post_lo), v(post_hi), v(counter), int(bool(z_reverse))))
 
     def apply_synced(self, G, F, op, ghost, epoch, stream=None):
         """One whole-slab apply whose neighbour synchronisation happens inside the kernel."""

@@ -182,7 +182,8 @@ class SlabCurl:
         wait_hi = f.ptr + 8 if hi is not None else None       # flags[1]: written by my upper neighbour
         post_lo = a.peer_ptr(f, lo) + 8 if lo is not None else None   # I am the UPPER neighbour of `lo`
         post_hi = a.peer_ptr(f, hi) if hi is not None else None       # I am the LOWER neighbour of `hi`
-        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16)
+        # ranks alternate the z-order of their CTAs: my first wave then faces the chunks my neighbour finished early
+        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16, z_reverse=(r % 2 == 1))
         self._flag_sync_ready = True
 
     def _apply_peer(self, G, F, op):
