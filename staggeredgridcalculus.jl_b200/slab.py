@@ -36,6 +36,9 @@ from . import _lib
 from .device import DeviceArray
 from .matrixfree import Operator
 
+import os as _os
+_EXPERIMENT = _os.environ.get("SGC_SLAB_EXPERIMENT", "")  # "nobarrier" | "noghost": development timing knobs
+
 __all__ = ["SlabCurl", "CudaBackend", "PeerArena", "halo_plan", "partition_planes", "row_range_for_rank"]
 
 
@@ -183,7 +186,8 @@ class SlabCurl:
         post_lo = a.peer_ptr(f, lo) + 8 if lo is not None else None   # I am the UPPER neighbour of `lo`
         post_hi = a.peer_ptr(f, hi) if hi is not None else None       # I am the LOWER neighbour of `hi`
         # ranks alternate the z-order of their CTAs: my first wave then faces the chunks my neighbour finished early
-        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16, z_reverse=(r % 2 == 1))
+        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16,
+                                      z_reverse=(r % 2 == 1) and _EXPERIMENT == "zreverse")
         self._flag_sync_ready = True
 
     def _apply_peer(self, G, F, op):
@@ -206,7 +210,10 @@ class SlabCurl:
             self.arena.epoch += 1
             self.backend.op.apply_synced(G, F, op, ghost, self.arena.epoch)
             return
-        self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
+        if _EXPERIMENT != "nobarrier" and _EXPERIMENT != "noghost":  # (timing experiments only: results are then invalid)
+            self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
+        if _EXPERIMENT == "noghost":
+            ghost = None
         self.backend.op.apply_range(G, F, op, 0, Nz, ghost)
 
     def apply(self, G, F, op="="):
