@@ -21,7 +21,28 @@ from ._lib import lib, check
 from .device import DeviceArray
 from .matrixfree import Operator
 
-__all__ = ["HostCurlCurl", "HostSlabCurlCurl", "bind_to_gpu_numa_node"]
+__all__ = ["HostCurlCurl", "HostSlabCurlCurl", "bind_to_gpu_numa_node", "pipeline_plan"]
+
+
+def pipeline_plan(nz: int, nchunks: int, lo_iface: bool = False, hi_iface: bool = False):
+    """Plane ranges of the z-chunked curl-of-curl pipeline (forward C₁, backward C₂, non-periodic slab faces).
+
+    Returns (steps, tail): `steps[c] = dict(h2d=(a, b), H=(kb, ke), E2=(kb2, ke))` — after chunk [a, b) of E has
+    arrived, H is computed on [kb, ke) (it needs E[k+1]) and E′ on [kb2, ke) (it needs H[k−1]), and E′[kb2:ke] is
+    copied out; empty ranges have kb >= ke.  `tail = dict(H=..., E2=[...])` lists the planes that need a
+    neighbour rank's data and are finished after the peer barrier: H[nz−1] with an upper interface, then E′[0]
+    with a lower interface and E′[nz−1] with an upper interface.  Every plane of H and of E′ appears exactly once."""
+    nchunks = max(1, min(int(nchunks), int(nz)))
+    cuts = [(nz * c) // nchunks for c in range(nchunks + 1)]
+    steps = []
+    for c, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+        kb = a - 1 if c > 0 else 0
+        ke = (nz - 1 if hi_iface else nz) if c == nchunks - 1 else b - 1
+        kb2 = max(kb, 1) if lo_iface else kb
+        steps.append(dict(h2d=(a, b), H=(kb, ke), E2=(kb2, ke)))
+    tail = dict(H=(nz - 1, nz) if hi_iface else None,
+                E2=([(0, 1)] if lo_iface else []) + ([(nz - 1, nz)] if hi_iface and not (lo_iface and nz == 1) else []))
+    return steps, tail
 
 
 class HostCurlCurl:
@@ -142,43 +163,39 @@ class HostSlabCurlCurl:
         hi_iface = self.s1.plan["recv_from"] is not None   # my top H plane needs the upper neighbour's E
         lo_iface = self.s2.plan["recv_from"] is not None   # my bottom E′ plane needs the lower neighbour's H
         c1, c2 = self.s1.backend.op, self.s2.backend.op
-        last = len(self.chunks) - 1
+        steps, tail = pipeline_plan(nz, len(self.chunks), lo_iface, hi_iface)
         start = torch.cuda.Event()
         start.record(torch.cuda.current_stream())
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_event(start)
-        for c, (a, b) in enumerate(self.chunks):
+        for st in steps:
+            a, b = st["h2d"]
             self._copy_planes(lib.sgc_memcpy_h2d, self.E, E_host, a, b, self.s_in)
             arrived = torch.cuda.Event()
             arrived.record(self.s_in)
             self.s_cmp.wait_event(arrived)
-            kb = a - 1 if c > 0 else 0
-            ke = (nz - 1 if hi_iface else nz) if c == last else b - 1
+            (kb, ke), (kb2, ke2) = st["H"], st["E2"]
             if ke > kb:
                 c1.apply_range(self.H, self.E, "=", kb, ke, None, stream=self.s_cmp)
-                kb2 = max(kb, 1) if lo_iface else kb
-                if ke > kb2:
-                    c2.apply_range(self.E2, self.H, "=", kb2, ke, None, stream=self.s_cmp)
-                    done = torch.cuda.Event()
-                    done.record(self.s_cmp)
-                    self.s_out.wait_event(done)
-                    self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, kb2, ke, self.s_out)
+            if ke2 > kb2:
+                c2.apply_range(self.E2, self.H, "=", kb2, ke2, None, stream=self.s_cmp)
+                done = torch.cuda.Event()
+                done.record(self.s_cmp)
+                self.s_out.wait_event(done)
+                self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, kb2, ke2, self.s_out)
         # the interface planes: every rank's E has landed → H top plane; every rank's H is complete → E′
         with torch.cuda.stream(self.s_cmp):
             self.s1.arena.barrier()
-            if hi_iface:
-                c1.apply_range(self.H, self.E, "=", nz - 1, nz, self._ghost(self.s1, self.E), stream=self.s_cmp)
+            if tail["H"]:
+                c1.apply_range(self.H, self.E, "=", tail["H"][0], tail["H"][1], self._ghost(self.s1, self.E), stream=self.s_cmp)
             self.s1.arena.barrier()
-            if lo_iface:
-                c2.apply_range(self.E2, self.H, "=", 0, 1, self._ghost(self.s2, self.H), stream=self.s_cmp)
-            if hi_iface:
-                c2.apply_range(self.E2, self.H, "=", nz - 1, nz, None, stream=self.s_cmp)
+            for (k0, k1) in tail["E2"]:
+                gh = self._ghost(self.s2, self.H) if (k0 == 0 and lo_iface) else None
+                c2.apply_range(self.E2, self.H, "=", k0, k1, gh, stream=self.s_cmp)
             self.s1.arena.barrier()  # nobody overwrites E / H of the next pass while a neighbour still reads them
         done = torch.cuda.Event()
         done.record(self.s_cmp)
         self.s_out.wait_event(done)
-        if lo_iface:
-            self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, 0, 1, self.s_out)
-        if hi_iface:
-            self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, nz - 1, nz, self.s_out)
+        for (k0, k1) in tail["E2"]:
+            self._copy_planes(lib.sgc_memcpy_d2h, self.E2, Out_host, k0, k1, self.s_out)
         self.s_out.synchronize()

@@ -36,10 +36,7 @@ from . import _lib
 from .device import DeviceArray
 from .matrixfree import Operator
 
-import os as _os
-_EXPERIMENT = _os.environ.get("SGC_SLAB_EXPERIMENT", "")  # "nobarrier" | "noghost": development timing knobs
-
-__all__ = ["SlabCurl", "CudaBackend", "PeerArena", "halo_plan", "partition_planes", "row_range_for_rank"]
+__all__ = ["SlabCurlCurl", "SlabCurl", "CudaBackend", "PeerArena", "halo_plan", "partition_planes", "row_range_for_rank"]
 
 
 def partition_planes(nz_total: int, world: int):
@@ -185,9 +182,8 @@ class SlabCurl:
         wait_hi = f.ptr + 8 if hi is not None else None       # flags[1]: written by my upper neighbour
         post_lo = a.peer_ptr(f, lo) + 8 if lo is not None else None   # I am the UPPER neighbour of `lo`
         post_hi = a.peer_ptr(f, hi) if hi is not None else None       # I am the LOWER neighbour of `hi`
-        # ranks alternate the z-order of their CTAs: my first wave then faces the chunks my neighbour finished early
-        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16,
-                                      z_reverse=(r % 2 == 1) and _EXPERIMENT == "zreverse")
+        # (z_reverse: alternating the CTA z-order by rank parity measured 2.7 % slower — left off)
+        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16, z_reverse=False)
         self._flag_sync_ready = True
 
     def _apply_peer(self, G, F, op):
@@ -210,10 +206,7 @@ class SlabCurl:
             self.arena.epoch += 1
             self.backend.op.apply_synced(G, F, op, ghost, self.arena.epoch)
             return
-        if _EXPERIMENT != "nobarrier" and _EXPERIMENT != "noghost":  # (timing experiments only: results are then invalid)
-            self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
-        if _EXPERIMENT == "noghost":
-            ghost = None
+        self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
         self.backend.op.apply_range(G, F, op, 0, Nz, ghost)
 
     def apply(self, G, F, op="="):
@@ -244,3 +237,50 @@ class SlabCurl:
             be.apply_range(G, F, op, kb + 1, Nz, None)
         be.comm_join()
         be.apply_range(G, F, op, kb, kb + 1, self.ghost)
+
+
+class SlabCurlCurl:
+    """Fused curl-of-curl `G OP C₂(C₁ F)` on a z-slab-decomposed grid: ONE kernel per rank and pass, the
+    intermediate field never leaves shared memory, and the planes −1 and Nz of F that the slab's edge needs are
+    read straight from the neighbours' memory (`PeerArena`) — at interior interfaces and, for a Bloch z boundary,
+    at the physical faces whose wrap-around partner is another rank.  Needs opposite z-directions in the two
+    curls (halo reach of one plane) and slabs of equal size.
+
+    `N`, `dlinv1[2]`, `dlinv2[2]` are LOCAL; `dz1_below` / `dz1_above` are the entries of the GLOBAL ∆z₁⁻¹ just
+    below / above this rank's slab (wrapping around for Bloch; None at a symmetric physical face)."""
+
+    def __init__(self, dtype_code, N, isfwd1, dlinv1, isfwd2, dlinv2, isbloch, e, rank, world, arena: "PeerArena | None",
+                 dz1_below=None, dz1_above=None, alpha1=1.0, alpha2=1.0):
+        if bool(isfwd1[2]) == bool(isfwd2[2]) and world > 1:
+            raise _lib.SgcError(_lib.SGC_ERR_INVALID, "slab-decomposed curl-of-curl needs opposite z-directions in the two curls")
+        self.rank, self.world, self.arena = rank, world, arena if world > 1 else None
+        self.N = tuple(int(n) for n in N)
+        self.esize = 16 if dtype_code == _lib.SGC_C128 else 8
+        self.c1 = Operator.curl(dtype_code, self.N, isfwd1, dlinv1, isbloch, e, alpha=alpha1)
+        self.c2 = Operator.curl(dtype_code, self.N, isfwd2, dlinv2, isbloch, e, alpha=alpha2)
+        last = world - 1
+        for c in (self.c1, self.c2):
+            c.set_slab(lo_interface=rank > 0, hi_interface=rank < last)
+        ring = bool(isbloch[2]) and world > 1
+        self.lo = rank - 1 if rank > 0 else (last if ring else None)   # who owns plane −1
+        self.hi = rank + 1 if rank < last else (0 if ring else None)    # who owns plane Nz
+        if world > 1:
+            if (self.lo is not None and dz1_below is None) or (self.hi is not None and dz1_above is None):
+                raise _lib.SgcError(_lib.SGC_ERR_INVALID, "dz1_below / dz1_above are needed wherever a neighbour rank exists")
+            self.c1.set_slab_coef(dz1_below if self.lo is not None else None, dz1_above if self.hi is not None else None)
+
+    def apply(self, G, F, op="="):
+        if self.arena is None:
+            self.c2.apply_after(self.c1, G, F, op)
+            return
+        plane = self.N[0] * self.N[1]
+        M = plane * self.N[2]
+        self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
+        glo = ghi = None
+        if self.lo is not None:
+            base = self.arena.peer_ptr(F, self.lo)
+            glo = [base + (c * M + (self.N[2] - 1) * plane) * self.esize for c in range(3)]
+        if self.hi is not None:
+            base = self.arena.peer_ptr(F, self.hi)
+            ghi = [base + c * M * self.esize for c in range(3)]
+        self.c2.apply_after(self.c1, G, F, op, ghost_lo=glo, ghost_hi=ghi)

@@ -123,3 +123,44 @@ def test_gridgen_reproduces_the_pml_closed_form():
     # symmetric grid: ghost dual point mirrored about the boundary (grid.jl:141)
     g2 = GG.Grid((np.array([0.0, 1.0, 3.0, 4.0]),), [False])
     assert np.array_equal(g2.dl[0][0], np.array([1.0, 1.5, 1.5]))
+
+
+@pytest.mark.parametrize("nz,nchunks", [(256, 16), (7, 3), (5, 8), (1, 4), (33, 1)])
+@pytest.mark.parametrize("lo_iface,hi_iface", [(False, False), (True, False), (False, True), (True, True)])
+def test_host_pipeline_plan_covers_every_plane_once(nz, nchunks, lo_iface, hi_iface):
+    """The z-chunked host pipeline (hostpipe.pipeline_plan): every plane of E is copied in once, every plane of H and
+    of E′ is computed exactly once, and no step uses data that has not arrived / been computed yet."""
+    import importlib.util
+    import os
+    import sys
+    import types
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    # hostpipe imports torch and the library binding; only the pure planning function is exercised here
+    src = open(os.path.join(here, "staggeredgridcalculus.jl_b200", "hostpipe.py")).read()
+    start = src.index("def pipeline_plan")
+    end = src.index("\nclass HostCurlCurl")
+    ns = {}
+    exec(src[start:end], ns)
+    steps, tail = ns["pipeline_plan"](nz, nchunks, lo_iface, hi_iface)
+    arrived = 0
+    H_done, E2_done = [0] * nz, [0] * nz
+    for st in steps:
+        a, b = st["h2d"]
+        assert a == arrived and b > a
+        arrived = b
+        kb, ke = st["H"]
+        for k in range(kb, max(kb, ke)):
+            assert k + 1 < arrived or k == nz - 1 and arrived == nz and not hi_iface, "H[k] needs E[k+1]"
+            H_done[k] += 1
+        kb2, ke2 = st["E2"]
+        for k in range(kb2, max(kb2, ke2)):
+            assert H_done[k] == 1 and (k == 0 or H_done[k - 1] == 1), "E'[k] needs H[k-1], H[k]"
+            E2_done[k] += 1
+    assert arrived == nz
+    if tail["H"]:
+        for k in range(*tail["H"]):
+            H_done[k] += 1
+    for rng_ in tail["E2"]:
+        for k in range(*rng_):
+            E2_done[k] += 1
+    assert H_done == [1] * nz and E2_done == [1] * nz

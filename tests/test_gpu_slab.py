@@ -142,3 +142,62 @@ def test_slab_flag_sync_chain_matches_single_gpu():
     results = mgr.dict()
     mp.spawn(_worker_flags, args=(world, _free_port(), results), nprocs=world, join=True)
     assert all(results.get(r) is True for r in range(world)), dict(results)
+
+
+def _worker_curlcurl(rank, world, port, results):
+    """Fused curl-of-curl across ranks (SlabCurlCurl: one kernel per rank, E planes −1 / Nz over peer memory) against
+    two single-GPU curls, for both z-direction pairings, Bloch (ring) and symmetric z boundaries, `=` and `+=`."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sgc_b200 as S
+        from sgc_b200.slab import SlabCurlCurl, PeerArena, partition_planes
+        rng = np.random.default_rng(7)
+        N = (70, 37, 5 * world)
+        F = np.asfortranarray(rng.uniform(-1, 1, N + (3,)) + 1j * rng.uniform(-1, 1, N + (3,)))
+        G0 = np.asfortranarray(rng.uniform(-1, 1, N + (3,)) + 1j * rng.uniform(-1, 1, N + (3,)))
+        d1 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+        d2 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+        e = [np.exp(-0.3j), np.exp(0.5j), np.exp(-0.9j)]
+        k0, k1 = partition_planes(N[2], world)[rank]
+        Nl = (N[0], N[1], k1 - k0)
+        arena = PeerArena(2 * 3 * N[0] * N[1] * (k1 - k0) * 16 + 1024)
+        Ga, Fa = arena.array(Nl + (3,)), arena.array(Nl + (3,))
+        ok = True
+        for fz1 in (True, False):
+            for bz in (True, False):
+                for op in ("=", "+="):
+                    isfwd1, isfwd2, isbloch = [True, False, fz1], [False, True, not fz1], [True, False, bz]
+                    w1 = S.Operator.curl(S.SGC_C128, N, isfwd1, d1, isbloch, e, alpha=0.5)
+                    w2 = S.Operator.curl(S.SGC_C128, N, isfwd2, d2, isbloch, e)
+                    H = S.DeviceArray.zeros(N + (3,))
+                    Gw = S.DeviceArray.from_numpy(G0)
+                    w1.apply(H, S.DeviceArray.from_numpy(F), "=")
+                    w2.apply(Gw, H, op)
+                    ref = Gw.numpy()[:, :, k0:k1, :]
+                    cc = SlabCurlCurl(S.SGC_C128, Nl, isfwd1, [d1[0], d1[1], d1[2][k0:k1]], isfwd2, [d2[0], d2[1], d2[2][k0:k1]],
+                                      isbloch, e, rank, world, arena, dz1_below=d1[2][(k0 - 1) % N[2]], dz1_above=d1[2][k1 % N[2]],
+                                      alpha1=0.5)
+                    arena.barrier()  # nobody may still be reading Fa from the previous case
+                    Ga.t.copy_(S.DeviceArray.from_numpy(np.asfortranarray(G0[:, :, k0:k1, :])).t)
+                    Fa.t.copy_(S.DeviceArray.from_numpy(np.asfortranarray(F[:, :, k0:k1, :])).t)
+                    cc.apply(Ga, Fa, op)
+                    torch.cuda.synchronize()
+                    ok = ok and np.array_equal(Ga.numpy(), ref)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_fused_curlcurl_matches_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_curlcurl, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert all(results.get(r) is True for r in range(world)), dict(results)
