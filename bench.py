@@ -186,6 +186,7 @@ def main():
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="side experiments only: skip the host-array leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--wc-input", action="store_true", help="experiment: write-combined pinned input buffer for the host-array leg")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="z-chunks of the host-array pipeline")
     ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] (2-D operators) and fused curl-of-curl side measurements")
     ap.add_argument("--serial-e2e", action="store_true", help="N > 1: H2D, step, D2H without the chunked pipeline")
@@ -319,7 +320,15 @@ def main():
     e2e_val, e2e_s, e2e_steps, e2e_mode = None, 0.0, 1, "skipped (--no-e2e)"
     if not args.no_e2e:
         c_dual.sync = c_prim.sync = "barrier"  # host copies touch the fields between applies: full barriers
-        E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+        from sgc_b200._lib import lib as _l, check as _c
+        import ctypes as _C
+        if args.wc_input:  # write-combined pinned input (the host only writes it, the GPU reads it)
+            hp = _C.c_void_p()
+            _c(_l.sgc_malloc_host_wc(_C.byref(hp), nbytes))
+            buf = (_C.c_double * (6 * M)).from_address(hp.value)
+            E_host = torch.view_as_complex(torch.from_numpy(np.ctypeslib.as_array(buf)).view(-1, 2))
+        else:
+            E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
         E_host.copy_(E.t)
         Out_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
         from sgc_b200._lib import lib, check

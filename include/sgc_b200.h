@@ -63,6 +63,8 @@ int sgc_set_device(int device);
 int sgc_malloc(void **dptr, size_t bytes);
 int sgc_free(void *dptr);
 int sgc_malloc_host(void **hptr, size_t bytes); /* pinned */
+/* pinned AND write-combined: for buffers the host only writes and the GPU reads (H2D sources) */
+int sgc_malloc_host_wc(void **hptr, size_t bytes);
 int sgc_free_host(void *hptr);
 int sgc_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
 int sgc_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);

@@ -65,6 +65,11 @@ extern "C" int sgc_malloc_host(void **hptr, size_t bytes) {
     CUDA_TRY(cudaMallocHost(hptr, bytes ? bytes : 1));
     return SGC_OK;
 }
+extern "C" int sgc_malloc_host_wc(void **hptr, size_t bytes) {
+    REQUIRE(hptr, "hptr is NULL");
+    CUDA_TRY(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
+    return SGC_OK;
+}
 extern "C" int sgc_free_host(void *hptr) {
     CUDA_TRY(cudaFreeHost(hptr));
     return SGC_OK;
