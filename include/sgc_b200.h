@@ -63,6 +63,9 @@ int sgc_set_device(int device);
 int sgc_malloc(void **dptr, size_t bytes);
 int sgc_free(void *dptr);
 int sgc_malloc_host(void **hptr, size_t bytes); /* pinned */
+/* Test hook: out[q] = z[q] / w[q] evaluated on the HOST by the library's own complex-division routine (Julia
+ * Base's scaled robust algorithm, the source the kernels compile); n (re, im) pairs. */
+int sgc_debug_cdiv(const double *z, const double *w, double *out, int64_t n);
 /* pinned AND write-combined: for buffers the host only writes and the GPU reads (H2D sources) */
 int sgc_malloc_host_wc(void **hptr, size_t bytes);
 int sgc_free_host(void *hptr);

@@ -65,6 +65,17 @@ extern "C" int sgc_malloc_host(void **hptr, size_t bytes) {
     CUDA_TRY(cudaMallocHost(hptr, bytes ? bytes : 1));
     return SGC_OK;
 }
+// Host evaluation of the library's complex division (the same source the kernels compile): lets the CPU tests pin
+// the restated Julia Base algorithm against published known-answer vectors.  n pairs (re, im) each.
+extern "C" int sgc_debug_cdiv(const double *z, const double *w, double *out, int64_t n) {
+    REQUIRE(z && w && out && n >= 0, "bad arguments");
+    for (int64_t q = 0; q < n; ++q) {
+        const cplx r = cdiv(cplx{z[2 * q], z[2 * q + 1]}, cplx{w[2 * q], w[2 * q + 1]});
+        out[2 * q] = r.re;
+        out[2 * q + 1] = r.im;
+    }
+    return SGC_OK;
+}
 extern "C" int sgc_malloc_host_wc(void **hptr, size_t bytes) {
     REQUIRE(hptr, "hptr is NULL");
     CUDA_TRY(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
