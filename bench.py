@@ -203,9 +203,11 @@ def main():
         run_reference(args, rank, world)
         return
 
-    # keep stdout for the ONE JSON line: NCCL's banner ("NCCL version …", printed at NCCL_DEBUG=VERSION/WARN) and
-    # any NCCL warning go to a per-process log file instead of stdout
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/nccl_debug.%h.%p.log")
+    # keep stdout for the ONE JSON line: whatever native libraries print while the job sets up (NCCL prints its
+    # version banner to stdout on some boxes) is sent to stderr; file descriptor 1 is restored for the result line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import sgc_b200 as S
@@ -437,8 +439,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         rate, threads, sample = cpu_reference_rate(dprim, ddual, NLOCAL[2], args.cpu_seconds)
         out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(out), flush=True)
     if world > 1:
+        os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
 
