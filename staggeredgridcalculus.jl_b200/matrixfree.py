@@ -64,7 +64,9 @@ class Operator:
         h = C.c_void_p()
         check(lib.sgc_op_create_mhat(C.byref(h), dtype_code, len(N), int64s(N), nw, int(isfwd), p1, p2, c1 or c2,
                                      int(isbloch), scalar2(e), scalar2(alpha)))
-        return cls(h, dtype_code, N, 1, 1, (k1, k2))
+        o = cls(h, dtype_code, N, 1, 1, (k1, k2))
+        o.weighted_axis = nw if dw is not None else None  # (the slab driver refuses weighted means along the slab axis)
+        return o
 
     @classmethod
     def curl(cls, dtype_code, N, isfwd, dlinv=None, isbloch=None, e=None, cmp_shp=None, cmp_out=None,

@@ -36,7 +36,7 @@ from . import _lib
 from .device import DeviceArray
 from .matrixfree import Operator
 
-__all__ = ["SlabCurlCurl", "SlabCurl", "CudaBackend", "PeerArena", "halo_plan", "partition_planes", "row_range_for_rank"]
+__all__ = ["SlabOp", "SlabCurlCurl", "SlabCurl", "CudaBackend", "PeerArena", "halo_plan", "partition_planes", "row_range_for_rank"]
 
 
 def partition_planes(nz_total: int, world: int):
@@ -284,3 +284,41 @@ class SlabCurlCurl:
             base = self.arena.peer_ptr(F, self.hi)
             ghi = [base + c * M * self.esize for c in range(3)]
         self.c2.apply_after(self.c1, G, F, op, ghost_lo=glo, ghost_hi=ghi)
+
+
+class SlabOp:
+    """Any matrix-free operator of the library (`Operator.partial / mhat / mean / divg / grad / curl`) on a grid that
+    is slab-decomposed along its LAST axis, with the one-plane halo read from the neighbour's memory (`PeerArena`):
+    `apply_∂!` / `apply_m̂!` along the slab axis need one plane of their input, `apply_divg!` one plane of the last
+    component, `apply_grad!` one plane of f; operators acting along other axes need nothing.
+
+    `op` is built on the LOCAL grid with the local slice of the slab-axis vectors; `isfwd_last` / `isbloch_last`
+    are the direction and the GLOBAL boundary type of the term(s) acting along the slab axis (None when the
+    operator has no such term); `ghost_comps` lists the input components those terms read."""
+
+    def __init__(self, op: Operator, isfwd_last, isbloch_last, ghost_comps, rank, world, arena: "PeerArena | None"):
+        if world > 1 and getattr(op, "weighted_axis", None) == len(op.N):
+            # the boundary weights ∆w[1] / ∆w[N] of mean.jl:516-527, :633-645 belong to the neighbour rank's slice
+            raise _lib.SgcError(_lib.SGC_ERR_INVALID, "a weighted mean along the slab axis is not supported across ranks")
+        self.op, self.rank, self.world = op, rank, world
+        self.arena = arena if world > 1 else None
+        self.ghost_comps = tuple(ghost_comps) if isfwd_last is not None else ()
+        self.plan = halo_plan(rank, world, bool(isfwd_last), bool(isbloch_last)) if isfwd_last is not None else None
+        op.set_slab(lo_interface=rank > 0, hi_interface=rank < world - 1)
+        self.esize = 16 if op.dtype_code == _lib.SGC_C128 else 8
+
+    def apply(self, G, F, op="="):
+        N = self.op.N
+        n_last = N[-1]
+        if self.arena is None:
+            self.op.apply_range(G, F, op, 0, n_last, None)
+            return
+        M = int(np.prod(N, dtype=np.int64))
+        plane = M // n_last
+        self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
+        ghost = None
+        if self.plan is not None and self.plan["recv_from"] is not None:
+            base = self.arena.peer_ptr(F, self.plan["recv_from"])
+            kpl = 0 if self.plan["boundary"] == "top" else n_last - 1
+            ghost = [base + (c * M + kpl * plane) * self.esize if c in self.ghost_comps else None for c in range(self.op.n_in)]
+        self.op.apply_range(G, F, op, 0, n_last, ghost)

@@ -201,3 +201,73 @@ def test_slab_fused_curlcurl_matches_single_gpu():
     results = mgr.dict()
     mp.spawn(_worker_curlcurl, args=(world, _free_port(), results), nprocs=world, join=True)
     assert all(results.get(r) is True for r in range(world)), dict(results)
+
+
+def _worker_slabop(rank, world, port, results):
+    """`SlabOp`: ∂z, m̂z, divergence, gradient and (no halo) ∂x, weighted m̂y on a z-slab-decomposed grid over peer memory,
+    against the single-GPU operators, forward / backward, Bloch (ring) / symmetric, `=` and `+=`."""
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import sgc_b200 as S
+        from sgc_b200.slab import SlabOp, PeerArena, partition_planes
+        rng = np.random.default_rng(8)
+        N = (40, 18, 4 * world)
+        k0, k1 = partition_planes(N[2], world)[rank]
+        Nl = (N[0], N[1], k1 - k0)
+        Ml = Nl[0] * Nl[1] * Nl[2]
+        d = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+        w = [rng.uniform(0.5, 1.5, n) for n in N]
+        e = [np.exp(-0.3j), np.exp(0.5j), np.exp(-0.9j)]
+        arena = PeerArena(2 * 3 * Ml * 16 + 1024)
+        cplx = lambda shape: np.asfortranarray(rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape))
+        loc = lambda v: [v[0], v[1], v[2][k0:k1]]
+        cut = lambda A: np.asfortranarray(A[:, :, k0:k1] if A.ndim == 3 else A[:, :, k0:k1, :])
+        ok = True
+        for fz in (True, False):
+            for bz in (True, False):
+                bl = [True, False, bz]
+                fw = [False, True, fz]
+                cases = [
+                    ("dz", N, N, lambda n, v: S.Operator.partial(S.SGC_C128, n, 3, fz, v(d)[2], bz, e[2], alpha=0.5), fz, bz, [0]),
+                    ("dx", N, N, lambda n, v: S.Operator.partial(S.SGC_C128, n, 1, fz, v(d)[0], True, e[0]), None, None, []),
+                    ("mz", N, N, lambda n, v: S.Operator.mhat(S.SGC_C128, n, 3, fz, None, None, bz, e[2], alpha=2.0), fz, bz, [0]),
+                    ("my weighted", N, N, lambda n, v: S.Operator.mhat(S.SGC_C128, n, 2, fz, v(w)[1], v(d)[1], False), None, None, []),
+                    ("divg", N, N + (3,), lambda n, v: S.Operator.divg(S.SGC_C128, n, fw, v(d), bl, e), fz, bz, [2]),
+                    ("grad", N + (3,), N, lambda n, v: S.Operator.grad(S.SGC_C128, n, fw, v(d), bl, e), fz, bz, [0]),
+                ]
+                for name, gshape, fshape, mk, f_last, b_last, gc in cases:
+                    F, G0 = cplx(fshape), cplx(gshape)
+                    for op in ("=", "+="):
+                        whole = mk(N, lambda v: v)
+                        Gw = S.DeviceArray.from_numpy(G0)
+                        whole.apply(Gw, S.DeviceArray.from_numpy(F), op)
+                        ref = cut(Gw.numpy())
+                        so = SlabOp(mk(Nl, loc), f_last, b_last, gc, rank, world, arena)
+                        arena.barrier()  # nobody may still be reading the arena fields of the previous case
+                        arena.used = 64  # re-carve (after the flags) for this case's shapes; all ranks do the same
+                        Ga, Fa = arena.array(cut(G0).shape), arena.array(cut(F).shape)
+                        Ga.t.copy_(S.DeviceArray.from_numpy(cut(G0)).t); Fa.t.copy_(S.DeviceArray.from_numpy(cut(F)).t)
+                        so.apply(Ga, Fa, op)
+                        torch.cuda.synchronize()
+                        good = np.array_equal(Ga.numpy(), ref)
+                        if not good:
+                            results[f"fail{rank}"] = f"{name} fz={fz} bz={bz} {op}"
+                        ok = ok and good
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_other_operators_match_single_gpu():
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker_slabop, args=(world, _free_port(), results), nprocs=world, join=True)
+    assert all(results.get(r) is True for r in range(world)), dict(results)
