@@ -127,6 +127,10 @@ int sgc_op_create_mean(sgc_op **op, int dtype, int ndim, const int64_t *N, const
  * face as an interior interface (the neighbour plane comes from another rank, no boundary
  * condition is applied there) instead of a physical boundary. */
 int sgc_op_set_slab(sgc_op *op, int lo_interface, int hi_interface);
+/* Weighted means along the slab axis: dw of the neighbour's plane just below / above the slab (one element
+ * each, re[,im]; the global wrap-around entries at Bloch faces), which the boundary formulas of
+ * matrixfree/mean.jl:516-527 / :633-645 read instead of the local table's first / last entry. */
+int sgc_op_set_slab_weights(sgc_op *op, const double *dw_below, const double *dw_above, int coef_complex);
 
 /* Kernel tuning knobs of the fused curl (0 keeps the default): tile size, z-march length, and
  * `variant`: low 4 bits select the kernel (0 = cp.async shared-memory ring [default], 1 =

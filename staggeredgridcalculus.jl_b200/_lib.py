@@ -67,6 +67,7 @@ _PROTOS = {
     "sgc_op_create_grad": (C.c_int, [vpp, C.c_int, C.c_int, i64p, intp, vpp, C.c_int, intp, dblp, dblp]),
     "sgc_op_create_mean": (C.c_int, [vpp, C.c_int, C.c_int, i64p, intp, vpp, vpp, C.c_int, intp, dblp, dblp]),
     "sgc_op_set_slab": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "sgc_op_set_slab_weights": (C.c_int, [C.c_void_p, dblp, dblp, C.c_int]),
     "sgc_op_set_tuning": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "sgc_op_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sgc_op_apply_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, C.c_int64, C.c_int64,

@@ -126,6 +126,9 @@ struct sgc_op {
     unsigned *sync_counter = nullptr;
     int sync_z_reverse = 0;
     mutable long long sync_epoch = 0;                // epoch of the apply being launched (0: plain apply)
+    // weighted means on a slab: ∆w of the neighbour's plane below / above (sgc_op_set_slab_weights)
+    bool has_slab_w = false;
+    HV slab_w[2] = {{1.0, 0.0, false}, {1.0, 0.0, false}};
     HV alpha = {1.0, 0.0, false};                    // α of a curl operator (for the ghost-plane coefficients)
     sgc::cplx cz_ghost[2] = {{1.0, 0.0}, {1.0, 0.0}};  // α·∆z⁻¹ of the planes −1 / Nz (slab neighbours)
     int tile_x = 0, tile_y = 0, march = 0, variant = 0;

@@ -359,6 +359,16 @@ extern "C" int sgc_op_set_slab(sgc_op *op, int lo_interface, int hi_interface) {
     return SGC_OK;
 }
 
+extern "C" int sgc_op_set_slab_weights(sgc_op *op, const double *dw_below, const double *dw_above, int coef_complex) {
+    REQUIRE(op, "op is NULL");
+    op->slab_w[0] = dw_below ? vec_at(dw_below, coef_complex, 0) : hv(1.0);
+    op->slab_w[1] = dw_above ? vec_at(dw_above, coef_complex, 0) : hv(1.0);
+    if (op->dtype == SGC_F64 && (op->slab_w[0].cx || op->slab_w[1].cx))
+        return fail(SGC_ERR_INEXACT, "complex ∆w with a Float64 field (InexactError)");
+    op->has_slab_w = true;
+    return SGC_OK;
+}
+
 extern "C" int sgc_op_set_tuning(sgc_op *op, int tile_x, int tile_y, int march_z, int variant) {
     REQUIRE(op, "op is NULL");
     op->tile_x = tile_x; op->tile_y = tile_y; op->march = march_z; op->variant = variant;
@@ -382,6 +392,14 @@ static int launch_term(const sgc_op *op, const Term &t, T *G, const T *F, const 
     p.w = (const C *)((const unsigned char *)op->arena + t.off_w);
     p.a2 = narrow<C>(t.a2); p.a1 = narrow<C>(t.a1); p.b0 = narrow<C>(t.b0);
     p.w_hi = narrow<C>(t.w_hi); p.w_lo = narrow<C>(t.w_lo);
+    if (op->has_slab_w && t.kind == KIND_MEAN_WEIGHTED && t.axis == op->ndim - 1) {
+        // the plane beyond the slab belongs to a neighbour rank: its ∆w replaces the local wrap-around entry;
+        // at a physical Bloch face the phase stays folded in (∆w[1]·e, mean.jl:524-527), at an interface it does not
+        HV ev = t.e_real ? hv(t.e.re) : hvc(t.e.re, t.e.im);
+        const HV whi = (t.bloch && !op->hi_iface) ? hmul(op->slab_w[1], ev) : op->slab_w[1];
+        p.w_hi = narrow<C>(to_cplx(whi));
+        p.w_lo = narrow<C>(to_cplx(op->slab_w[0]));
+    }
     p.e = t.e; p.e_real = t.e_real; p.fwd = t.fwd;
     p.inner = 1;
     for (int d = 0; d < a; ++d) p.inner *= op->N[d];

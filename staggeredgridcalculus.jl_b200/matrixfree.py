@@ -205,6 +205,15 @@ class Operator:
     def set_slab(self, lo_interface: bool, hi_interface: bool):
         check(lib.sgc_op_set_slab(self._h, int(lo_interface), int(hi_interface)))
 
+    def set_slab_weights(self, dw_below, dw_above):
+        """∆w of the neighbour rank's plane just below / above this slab (weighted means along the slab axis)."""
+        cc = int(any(np.iscomplexobj(np.asarray(v)) for v in (dw_below, dw_above)))
+        def pack(v):
+            z = complex(v)
+            return (C.c_double * 2)(z.real, z.imag) if cc else (C.c_double * 1)(float(np.real(v)))
+        check(lib.sgc_op_set_slab_weights(self._h, pack(dw_below), pack(dw_above), cc))
+        self.weighted_axis = None  # the slab driver may now take it
+
     def set_tuning(self, tile_x=0, tile_y=0, march_z=0, variant=0):
         check(lib.sgc_op_set_tuning(self._h, tile_x, tile_y, march_z, variant))
 

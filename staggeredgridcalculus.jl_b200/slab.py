@@ -299,7 +299,8 @@ class SlabOp:
     def __init__(self, op: Operator, isfwd_last, isbloch_last, ghost_comps, rank, world, arena: "PeerArena | None"):
         if world > 1 and getattr(op, "weighted_axis", None) == len(op.N):
             # the boundary weights ∆w[1] / ∆w[N] of mean.jl:516-527, :633-645 belong to the neighbour rank's slice
-            raise _lib.SgcError(_lib.SGC_ERR_INVALID, "a weighted mean along the slab axis is not supported across ranks")
+            raise _lib.SgcError(_lib.SGC_ERR_INVALID, "a weighted mean along the slab axis needs the neighbours' ∆w: "
+                                "call op.set_slab_weights(dw_below, dw_above) first")
         self.op, self.rank, self.world = op, rank, world
         self.arena = arena if world > 1 else None
         self.ghost_comps = tuple(ghost_comps) if isfwd_last is not None else ()

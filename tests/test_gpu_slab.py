@@ -203,6 +203,13 @@ def test_slab_fused_curlcurl_matches_single_gpu():
     assert all(results.get(r) is True for r in range(world)), dict(results)
 
 
+def _weighted_mz(S, n, fz, wl, dl, bz, ez, w_global, k0, k1, is_slab):
+    o = S.Operator.mhat(S.SGC_C128, n, 3, fz, wl, dl, bz, ez)
+    if is_slab:  # the neighbours' ∆w just below / above the slab (wrapping around the global grid)
+        o.set_slab_weights(w_global[(k0 - 1) % len(w_global)], w_global[k1 % len(w_global)])
+    return o
+
+
 def _worker_slabop(rank, world, port, results):
     """`SlabOp`: ∂z, m̂z, divergence, gradient and (no halo) ∂x, weighted m̂y on a z-slab-decomposed grid over peer memory,
     against the single-GPU operators, forward / backward, Bloch (ring) / symmetric, `=` and `+=`."""
@@ -235,6 +242,7 @@ def _worker_slabop(rank, world, port, results):
                     ("dz", N, N, lambda n, v: S.Operator.partial(S.SGC_C128, n, 3, fz, v(d)[2], bz, e[2], alpha=0.5), fz, bz, [0]),
                     ("dx", N, N, lambda n, v: S.Operator.partial(S.SGC_C128, n, 1, fz, v(d)[0], True, e[0]), None, None, []),
                     ("mz", N, N, lambda n, v: S.Operator.mhat(S.SGC_C128, n, 3, fz, None, None, bz, e[2], alpha=2.0), fz, bz, [0]),
+                    ("mz weighted", N, N, lambda n, v: _weighted_mz(S, n, fz, v(w)[2], v(d)[2], bz, e[2], w[2], k0, k1, n != N), fz, bz, [0]),
                     ("my weighted", N, N, lambda n, v: S.Operator.mhat(S.SGC_C128, n, 2, fz, v(w)[1], v(d)[1], False), None, None, []),
                     ("divg", N, N + (3,), lambda n, v: S.Operator.divg(S.SGC_C128, n, fw, v(d), bl, e), fz, bz, [2]),
                     ("grad", N + (3,), N, lambda n, v: S.Operator.grad(S.SGC_C128, n, fw, v(d), bl, e), fz, bz, [0]),
