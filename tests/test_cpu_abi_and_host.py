@@ -164,3 +164,29 @@ def test_host_pipeline_plan_covers_every_plane_once(nz, nchunks, lo_iface, hi_if
         for k in range(*rng_):
             E2_done[k] += 1
     assert H_done == [1] * nz and E2_done == [1] * nz
+
+
+def test_product_never_touches_the_oracle_and_binding_matches_header():
+    """Static checks of the boundary: (1) nothing under the product package (Python, C++/CUDA, Julia shim) imports,
+    includes, links or names the oracle; (2) every prototype of include/sgc_b200.h has a ctypes declaration in
+    `_lib.py` with the same number of parameters."""
+    import os
+    import re
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(here, "staggeredgridcalculus.jl_b200")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")) or f == "Makefile":
+                text = open(os.path.join(root, f), encoding="utf-8").read()
+                assert not re.search(r"\boracle\b|sgc_oracle|libsgc_oracle", text), f"{f} refers to the oracle"
+    header = open(os.path.join(here, "include", "sgc_b200.h"), encoding="utf-8").read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char \*)\s*(sgc_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)
+    assert len(protos) >= 50
+    import sgc_b200
+    table = sgc_b200._lib._PROTOS
+    for name, params in protos:
+        assert name in table, f"{name} is declared in the header but has no ctypes prototype"
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert len(table[name][1]) == n, f"{name}: header has {n} parameters, _lib.py declares {len(table[name][1])}"
