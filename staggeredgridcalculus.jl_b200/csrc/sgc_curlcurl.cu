@@ -111,7 +111,7 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
     const int version = c2->variant & 0xF;
     const int tx = (version == 1 && c2->tile_x) ? c2->tile_x : 32;
     const int ty = c2->tile_y ? c2->tile_y : (version == 1 ? 8 : 7);  // 32x7 outputs + 1 halo row = 8 warps, 2 CTAs/SM at 128 registers
-    const int se = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 3;
+    const int se = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : (sizeof(T) == 8 && version != 1 ? 4 : 3);  // Float64: 3 CTAs/SM, deeper ring
     const int64_t nk = k_end - k_begin;
     p.march = c2->march > 0 ? c2->march : (nk >= 256 ? 64 : 32);  // z-halo overhead (n+2)/n planes vs. number of CTAs
     dim3 grid((unsigned)((p.Nx + tx - 1) / tx), (unsigned)((p.Ny + ty - 1) / ty), (unsigned)((nk + p.march - 1) / p.march));

@@ -436,8 +436,9 @@ SGC_D void curl_point(int flags, C cxs, C cys, bool fx, bool fy, C cz, const cpl
     }
 }
 
+// resident CTAs per SM: 2 for ComplexF64 (128 registers), 3 for Float64 fields (half the registers and shared memory)
 template <typename T, typename C, bool ADD, int TY, int SE, bool FZ1, bool FZ2>
-__global__ void __launch_bounds__(32 * (TY + 1), 2) k_curlcurl3w(const __grid_constant__ CurlCurlParams<T, C> p) {
+__global__ void __launch_bounds__(32 * (TY + 1), (sizeof(T) == 8 ? 3 : 2)) k_curlcurl3w(const __grid_constant__ CurlCurlParams<T, C> p) {
     static_assert(SE >= 3, "need at least 3 stages");
     constexpr int TX = 32;
     constexpr int NT = 32 * (TY + 1);
