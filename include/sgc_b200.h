@@ -66,6 +66,9 @@ int sgc_malloc_host(void **hptr, size_t bytes); /* pinned */
 /* Test hook: out[q] = z[q] / w[q] evaluated on the HOST by the library's own complex-division routine (Julia
  * Base's scaled robust algorithm, the source the kernels compile); n (re, im) pairs. */
 int sgc_debug_cdiv(const double *z, const double *w, double *out, int64_t n);
+/* Test hook: out[q] = inv(w[q]) by the library's host routine for `e^(-1.0)` (Julia Base's scaled robust_cinv,
+ * with the multiply-add NOT fused), used for backward Bloch blocks of the assembly. */
+int sgc_debug_cinv(const double *w, double *out, int64_t n);
 /* pinned AND write-combined: for buffers the host only writes and the GPU reads (H2D sources) */
 int sgc_malloc_host_wc(void **hptr, size_t bytes);
 int sgc_free_host(void *hptr);

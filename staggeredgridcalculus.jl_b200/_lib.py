@@ -47,6 +47,7 @@ _PROTOS = {
     "sgc_malloc": (C.c_int, [vpp, C.c_size_t]),
     "sgc_free": (C.c_int, [C.c_void_p]),
     "sgc_malloc_host": (C.c_int, [vpp, C.c_size_t]),
+    "sgc_debug_cinv": (C.c_int, [dblp, dblp, C.c_int64]),
     "sgc_debug_cdiv": (C.c_int, [dblp, dblp, dblp, C.c_int64]),
     "sgc_malloc_host_wc": (C.c_int, [vpp, C.c_size_t]),
     "sgc_free_host": (C.c_int, [C.c_void_p]),

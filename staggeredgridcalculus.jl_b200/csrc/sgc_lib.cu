@@ -76,6 +76,15 @@ extern "C" int sgc_debug_cdiv(const double *z, const double *w, double *out, int
     }
     return SGC_OK;
 }
+extern "C" int sgc_debug_cinv(const double *w, double *out, int64_t n) {
+    REQUIRE(w && out && n >= 0, "bad arguments");
+    for (int64_t q = 0; q < n; ++q) {
+        const cplx r = cinv_host(cplx{w[2 * q], w[2 * q + 1]});
+        out[2 * q] = r.re;
+        out[2 * q + 1] = r.im;
+    }
+    return SGC_OK;
+}
 extern "C" int sgc_malloc_host_wc(void **hptr, size_t bytes) {
     REQUIRE(hptr, "hptr is NULL");
     CUDA_TRY(cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocWriteCombined));
