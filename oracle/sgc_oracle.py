@@ -221,6 +221,11 @@ def jl_inv(w) -> JV:
     c[big] *= 0.5; d[big] *= 0.5; s[big] = 0.5
     c[small] *= bs; d[small] *= bs; s[small] = bs
 
+    # Base's robust_cinv writes `muladd(d, r, c)`, which LLVM contracts to one FMA where the host has the
+    # instruction and leaves as a multiply and an add where it has not.  Which of the two the reference's own
+    # machine produces cannot be determined here; this restatement (and the CUDA library's host routine, which the
+    # tests hold bit-identical to it) evaluates it unfused.  The two differ by at most one rounding of `p`, i.e.
+    # within the 4-ulp budget of the north star, and only in `inv(e⁻ⁱᵏᴸ)` of backward Bloch blocks.
     def cinv(cc, dd):  # robust_cinv: r = d/c; p = inv(muladd(d, r, c)); q = -r*p
         with np.errstate(all="ignore"):
             r = dd / cc
