@@ -198,6 +198,38 @@ def test_row_partition_on_a_tall_grid_skips_far_columns(S):
                 assert np.array_equal(stacked.data, full.data), what
 
 
+@pytest.mark.parametrize("isfwd", [[True, True, True], [True, False, True]])
+def test_curl_of_curl_invariants_with_device_matrices(S, isfwd):
+    """test/curl.jl:123-186 with the matrices assembled on the GPU: `Cv*Cu` has diagonal 4, 13 nonzeros per row, is
+    Hermitian with ±1 off-diagonals; each block of Cu equals −(block of Cv)ᴴ; and `Cv*(Cu*f)` equals the fused
+    curl-of-curl kernel applied to f (block ordering)."""
+    import torch
+    N = (3, 4, 5)
+    M = 60
+    ones = [np.ones(n) for n in N]
+    nisfwd = [not b for b in isfwd]
+    Cu = S.create_curl(isfwd, ones, [True, False, False], np.ones(3), order_cmpfirst=False, index_base=0).to_scipy().toarray()
+    Cv = S.create_curl(nisfwd, ones, [True, False, False], np.ones(3), order_cmpfirst=False, index_base=0).to_scipy().toarray()
+    for i in range(3):
+        for j in ((i + 1) % 3, (i + 2) % 3):
+            assert np.array_equal(-Cv[i * M:(i + 1) * M, j * M:(j + 1) * M].conj().T, Cu[i * M:(i + 1) * M, j * M:(j + 1) * M])
+    Au = S.create_curl(isfwd, ones, [True] * 3, np.ones(3), order_cmpfirst=False)
+    Av = S.create_curl(nisfwd, ones, [True] * 3, np.ones(3), order_cmpfirst=False)
+    A = Av.to_scipy().toarray() @ Au.to_scipy().toarray()
+    assert np.all(np.diag(A) == 4)
+    assert np.all((A != 0).sum(axis=1) == 13)
+    assert np.array_equal(A, A.conj().T)
+    B = A - 4 * np.eye(A.shape[0])
+    assert np.all(np.abs(B[B != 0]) == 1)
+    rng = np.random.default_rng(18)
+    f = rand_field(rng, N + (3,), False)
+    fd = S.DeviceArray.from_numpy(f)
+    g = S.DeviceArray.zeros(N + (3,), np.float64)
+    S.apply_curlcurl(g, fd, "=", isfwd, ones, nisfwd, ones, [True] * 3, [1.0] * 3)
+    via_matrices = Av.matvec(Au.matvec(fd.t))
+    assert torch.allclose(via_matrices, g.t, rtol=1e-13, atol=1e-13)
+
+
 def test_csc_hand_off_formats(S, tmp_path):
     """pinned host arrays for the `SparseMatrixCSC(m,n,colptr,rowval,nzval)` constructor and the
     on-disk `.npz` dump, both equal to the oracle's matrix."""
