@@ -190,3 +190,24 @@ def test_product_never_touches_the_oracle_and_binding_matches_header():
         params = params.strip()
         n = 0 if params in ("", "void") else len(params.split(","))
         assert len(table[name][1]) == n, f"{name}: header has {n} parameters, _lib.py declares {len(table[name][1])}"
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """`bench.py --impl reference` (the reference's CPU algorithm, C/OpenMP port) runs without a GPU and prints exactly
+    one JSON line carrying the keys of the bench contract."""
+    import json
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(here, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--slab", "64,64,64"], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr[-500:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
