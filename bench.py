@@ -431,6 +431,17 @@ def main():
     if world == 1 and not args.no_assembly:
         out["assembly"] = bench_assembly(S, torch, peak)
         out["assembly_c128"] = bench_assembly(S, torch, peak, cplx=True)
+        if not args.no_cpu_baseline and "error" not in out["assembly"]:
+            # the reference's assembly algorithm (create_∂info temporaries → COO → serial counting-sort `sparse` →
+            # `dropzeros!`; C port, single thread like the stdlib) on a 128³ sample of the same matrix family
+            try:
+                from oracle import c_oracle as CO
+                n = 128
+                dt, nnz_cpu = CO.time_create_curl([True] * 3, [np.ones(n)] * 3, [True] * 3, [1.0] * 3)
+                out["assembly"]["cpu_baseline"] = {"value": nnz_cpu / dt, "unit": "nnz/s", "cores": 1, "kind": "port",
+                                                   "sample": f"create_curl {n}^3 Float64 all-Bloch ({nnz_cpu} nnz) in {dt:.2f} s"}
+            except Exception as ex:
+                out["assembly"]["cpu_baseline"] = {"error": str(ex)[:120]}
     if world == 1 and not args.no_extras:
         E_host = Out_host = None  # release the pinned staging arrays
         out["other_configs"] = bench_other_configs(S, torch, peak, c_dual.backend.op, c_prim.backend.op, E, E2, ms_step)
