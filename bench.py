@@ -29,21 +29,47 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-NLOCAL = (256, 256, 256)   # per-GPU slab
+NLOCAL = (256, 256, 256)   # per-GPU slab of the headline workload (BASELINE configs[1])
+CFG5 = (1024, 1024, 128)   # per-GPU slab of BASELINE configs[4]: 1024^3 over 8 GPUs
 NPML = 10
 ALG_BYTES_PER_CELL = 96    # one curl, OP '=': read 3 + write 3 ComplexF64 components
 
 
-def build_inputs(nz_total, seed=20260):
+def load_gridgen():
+    """gridgen.py as a standalone module (numpy only): the reference arm builds its inputs without importing the
+    package, i.e. without loading libsgc_b200.so."""
+    import importlib.util
+    path = os.path.join(ROOT, "staggeredgridcalculus.jl_b200", "gridgen.py")
+    spec = importlib.util.spec_from_file_location("sgc_gridgen_standalone", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def build_inputs(nz_total, seed=20260, nlocal=None):
     """Seeded nonuniform grid + PML stretch (host, O(ΣN)); returns ∆l⁻¹ at (primal, dual) points."""
-    from sgc_b200 import gridgen as GG
+    GG = load_gridgen()
+    nl = nlocal or NLOCAL
     rng = np.random.default_rng(seed)
-    lprim = [GG.graded_lprim(NLOCAL[0], rng), GG.graded_lprim(NLOCAL[1], rng), GG.graded_lprim(nz_total, rng)]
+    lprim = [GG.graded_lprim(nl[0], rng), GG.graded_lprim(nl[1], rng), GG.graded_lprim(nz_total, rng)]
     grid = GG.Grid(lprim, [False, False, False])
     mean_cell = np.mean([np.mean(np.diff(l)) for l in lprim])
     omega = 2 * np.pi / (20 * mean_cell)
     sdl = GG.create_stretched_dl(omega, grid, ([NPML] * 3, [NPML] * 3))
     return GG.invert_dl(sdl)
+
+
+def ulp_report(got, ref):
+    """(max error in ulp of the reference element's magnitude, number of elements that differ); +0.0 == -0.0.
+    Same metric as tests/util.py::max_ulp_error, evaluated on the differing elements only."""
+    if np.array_equal(got, ref):
+        return 0.0, 0
+    bad = got != ref
+    g, r = got[bad], ref[bad]
+    mag = np.maximum(np.abs(r), np.finfo(np.float64).tiny)
+    ulp = np.spacing(mag)
+    err = np.maximum(np.abs(g.real - r.real), np.abs(g.imag - r.imag)) / ulp
+    return float(err.max()), int(bad.sum())
 
 
 class ClockSampler(threading.Thread):
@@ -161,14 +187,248 @@ def run_reference(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(n):
-    fld_mb = NLOCAL[0] * NLOCAL[1] * NLOCAL[2] * 3 * 16 / 1e6
-    return {"workload": f"{NLOCAL[0]}x{NLOCAL[1]}x{NLOCAL[2] * n} nonuniform Yee grid, PML-stretched complex dl (Npml=10), PEC outer "
+def workload_config(n, nl=None):
+    nl = nl or NLOCAL
+    fld_mb = nl[0] * nl[1] * nl[2] * 3 * 16 / 1e6
+    return {"workload": f"{nl[0]}x{nl[1]}x{nl[2] * n} nonuniform Yee grid, PML-stretched complex dl (Npml=10), PEC outer "
                         f"boundaries, ComplexF64 curl-of-curl E->H->E' = 2 apply_curl! per step"
-                        + (f", z-slab decomposed over {n} GPUs ({NLOCAL[0]}x{NLOCAL[1]}x{NLOCAL[2]} per GPU) with one-plane halos" if n > 1 else ""),
-            "cells_per_gpu": NLOCAL[0] * NLOCAL[1] * NLOCAL[2], "curl_applies_per_step": 2,
+                        + (f", z-slab decomposed over {n} GPUs ({nl[0]}x{nl[1]}x{nl[2]} per GPU) with one-plane halos" if n > 1 else ""),
+            "cells_per_gpu": nl[0] * nl[1] * nl[2], "curl_applies_per_step": 2,
             "l2_policy": f"inputs_larger_than_L2 (3 fields x {fld_mb:.0f} MB per GPU vs 126 MB L2)",
             "parallelism": f"zslab{n}"}
+
+
+class Leg:
+    """One weak-scaling leg of the benchmark: a per-GPU slab `nl` of a grid that is z-slab decomposed over `world`
+    ranks, the two curl operators of the curl-of-curl pass, and the three fields E, H, E'."""
+
+    def __init__(self, S, torch, dist, nl, rank, world, args, seed_shift=0):
+        from sgc_b200.slab import SlabCurl
+        self.S, self.torch, self.dist = S, torch, dist
+        self.nl, self.rank, self.world = tuple(nl), rank, world
+        self.M = nl[0] * nl[1] * nl[2]
+        self.nz_total = nl[2] * world
+        self.dprim, self.ddual = build_inputs(self.nz_total, nlocal=nl)
+        self.k0, self.k1 = rank * nl[2], (rank + 1) * nl[2]
+        k0, k1, M = self.k0, self.k1, self.M
+        bl, e = [False] * 3, [1.0] * 3
+        # N > 1: fields live in peer-mapped memory (sgc_comm, CUDA IPC) and the fused kernel reads its one-plane
+        # halo straight from the neighbour over NVLink; NCCL send/recv is the fallback transport.
+        self.arena, self.halo = None, "none"
+        if world > 1 and args.halo == "peer":
+            try:
+                from sgc_b200.slab import PeerArena
+                self.arena = PeerArena(3 * 3 * M * 16 + 4096)
+                self.halo = f"peer-memory loads inside the stencil kernel (sgc_comm, mapping: {self.arena.backend}, NVLink)"
+            except Exception as ex:
+                sys.stderr.write(f"[bench] peer memory unavailable ({type(ex).__name__}: {str(ex)[:160]}); using NCCL halos\n")
+        if world > 1 and self.arena is None:
+            self.halo = "NCCL send/recv on a side stream, overlapped with the interior planes"
+        self.sync = args.sync if self.arena is not None else "barrier"
+        if self.arena is not None:
+            self.halo += ("; neighbour synchronisation inside the kernel (flags over NVLink, boundary chunks last), no barrier kernel"
+                          if self.sync == "flags" else "; sgc_peer_barrier kernel before every apply")
+        self.c_dual = SlabCurl(S.SGC_C128, nl, [True] * 3, [self.ddual[0], self.ddual[1], self.ddual[2][k0:k1]], bl, e, rank, world,
+                               arena=self.arena, sync=self.sync)
+        self.c_prim = SlabCurl(S.SGC_C128, nl, [False] * 3, [self.dprim[0], self.dprim[1], self.dprim[2][k0:k1]], bl, e, rank, world,
+                               arena=self.arena, sync=self.sync)
+        gen = torch.Generator(device="cuda").manual_seed(1234 + rank + seed_shift)
+
+        def rnd():
+            return torch.complex(torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1,
+                                 torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
+        if self.arena is not None:
+            self.E, self.H, self.E2 = (self.arena.array(self.nl + (3,)) for _ in range(3))
+            self.E.t.copy_(rnd()); self.H.t.zero_(); self.E2.t.zero_()
+        else:
+            self.E = S.DeviceArray(rnd(), self.nl + (3,))
+            self.H = S.DeviceArray.zeros(self.nl + (3,))
+            self.E2 = S.DeviceArray.zeros(self.nl + (3,))
+        self.barrier()
+
+    def step(self):
+        self.c_dual.apply(self.H, self.E, "=")
+        self.c_prim.apply(self.E2, self.H, "=")
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def resync(self):
+        """Something other than the synchronised applies touched the fields (or read them on the host)."""
+        self.barrier()
+        if self.arena is not None:
+            self.arena.barrier()
+
+    # ---- parity: this rank's planes against the C oracle (reference algorithm on the host) ------------------------
+    def parity(self, ranges=None):
+        """Runs one pass and compares E' on the local plane ranges [a, b) (default: the whole slab) with the C
+        restatement of the reference (six sweeps per apply_curl!, oracle/sgc_oracle_c.c) evaluated on the same E:
+        the oracle sees the planes [a−2, b+2) of the GLOBAL grid (the neighbours' edge planes are gathered), so
+        slab interfaces are checked against a computation that knows nothing about slabs."""
+        torch, dist = self.torch, self.dist
+        from oracle import c_oracle as CO
+        CO.set_threads(max(1, len(os.sched_getaffinity(0)) // self.world))
+        nx, ny, nz = self.nl
+        plane = nx * ny
+        self.resync()
+        self.step()
+        self.resync()
+        E = self.E.numpy()
+        got = self.E2.numpy()
+        Et = self.E.t.view(3, nz, plane)
+        edge = torch.stack([Et[:, :2, :], Et[:, nz - 2:, :]]).contiguous()  # (lo/hi side, comp, 2 planes, plane)
+        edges = [edge]
+        if self.world > 1:
+            edges = [torch.empty_like(edge) for _ in range(self.world)]
+            dist.all_gather(edges, edge)
+
+        def nb_planes(r, side):  # (nx, ny, 2, 3) planes at the lower / upper end of rank r's slab
+            a = edges[r][side].cpu().numpy()  # (3, 2, plane)
+            return np.asfortranarray(np.transpose(a.reshape(3, 2, ny, nx), (3, 2, 1, 0)))
+
+        worst, ndiff, cells = 0.0, 0, 0
+        for (a, b) in (ranges or [(0, nz)]):
+            ga, gb = self.k0 + a, self.k0 + b
+            lo, hi = max(ga - 2, 0), min(gb + 2, self.nz_total)
+            parts = []
+            if lo < self.k0:
+                parts.append(nb_planes(self.rank - 1, 1)[:, :, 2 - (self.k0 - lo):, :])
+            parts.append(E[:, :, max(lo, self.k0) - self.k0:min(hi, self.k1) - self.k0, :])
+            if hi > self.k1:
+                parts.append(nb_planes(self.rank + 1, 0)[:, :, :hi - self.k1, :])
+            Ex = np.asfortranarray(np.concatenate(parts, axis=2))
+            Hx, E2x = np.zeros_like(Ex), np.zeros_like(Ex)
+            dd = [self.ddual[0], self.ddual[1], self.ddual[2][lo:hi]]
+            dp = [self.dprim[0], self.dprim[1], self.dprim[2][lo:hi]]
+            CO.apply_curl(Hx, Ex, "=", [True] * 3, dd, [False] * 3, [1.0] * 3)
+            CO.apply_curl(E2x, Hx, "=", [False] * 3, dp, [False] * 3, [1.0] * 3)
+            err, nd = ulp_report(got[:, :, a:b, :], E2x[:, :, ga - lo:gb - lo, :])
+            worst, ndiff, cells = max(worst, err), ndiff + nd, cells + (b - a) * plane
+        t = torch.tensor([worst, -float(ndiff), -float(cells)], device="cuda", dtype=torch.float64)
+        if self.world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            worst, ndiff, cells = float(tmax[0]), int(-t[1]), int(-t[2])
+        return {"against": "C restatement of the reference's apply_curl! (oracle/sgc_oracle_c.c) on the same E, all ranks",
+                "max_ulp": worst, "cells": cells, "elements_differing": ndiff, "tolerance_ulp": 4, "ok": bool(worst <= 4.0)}
+
+    # ---- timing ---------------------------------------------------------------------------------------------------
+    def time(self, steps, warmup, use_graph, local_rank):
+        torch, dist, S = self.torch, self.dist, self.S
+        self.resync()
+        for _ in range(warmup):
+            self.step()
+        self.barrier()
+        graph, launches_per_step, run_step = None, None, self.step
+        if use_graph:
+            try:
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    g = torch.cuda.CUDAGraph()
+                    l0 = S.launch_count()
+                    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                        self.step()
+                    launches_per_step = S.launch_count() - l0
+                torch.cuda.current_stream().wait_stream(side)
+                graph = g
+            except Exception as ex:  # capture unsupported for some op: stay eager
+                sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:160]}); running eagerly\n")
+                graph = None
+                torch.cuda.synchronize()
+            ok = torch.tensor([1 if graph is not None else 0], device="cuda")
+            if self.world > 1:  # all ranks must take the same path
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                graph = None
+            if graph is not None:
+                run_step = graph.replay
+                for _ in range(2):
+                    run_step()
+        self.barrier()
+        launches0 = S.launch_count()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        t_host0 = time.perf_counter()
+        for _ in range(steps):
+            run_step()
+        host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps
+        ev1.record()
+        self.barrier()
+        ms_mine = ev0.elapsed_time(ev1) / steps
+        clocks = sampler.result()
+        launches = (launches_per_step * steps) if graph is not None else (S.launch_count() - launches0)
+        per_rank = [ms_mine]
+        if self.world > 1:
+            t = torch.tensor([ms_mine], device="cuda", dtype=torch.float64)
+            allt = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(allt, t)
+            per_rank = [float(x.item()) for x in allt]
+        ms_step = max(per_rank)
+        return {"ms_step": ms_step, "per_rank_ms": [round(x, 4) for x in per_rank], "clocks": clocks, "launches": int(launches),
+                "graph": graph is not None, "host_enqueue_ms": host_enqueue_ms,
+                "value": 2 * self.M * self.world / (ms_step * 1e-3) / 1e9}
+
+    def close(self):
+        self.barrier()
+        self.E = self.H = self.E2 = None
+        self.c_dual = self.c_prim = None
+        if self.arena is not None:
+            self.arena.close()
+            self.arena = None
+        self.torch.cuda.empty_cache()
+
+
+def small_bloch_parity(S, torch, dist, rank, world):
+    """A small all-Bloch grid (phases on every axis, z ring across the ranks): each rank's slab of E' = C₂(C₁ E),
+    through the same peer-memory / in-kernel-synchronised path as the timed step, against the C oracle on the whole
+    grid — exercises the wrap-around halo (raw plane from the far rank, phase applied in the kernel)."""
+    from oracle import c_oracle as CO
+    from sgc_b200.slab import SlabCurl, PeerArena
+    CO.set_threads(max(1, len(os.sched_getaffinity(0)) // world))
+    nl = (64, 48, 8)
+    N = (nl[0], nl[1], nl[2] * world)
+    rng = np.random.default_rng(77)
+    E = np.asfortranarray(rng.uniform(-1, 1, N + (3,)) + 1j * rng.uniform(-1, 1, N + (3,)))
+    d1 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+    d2 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-0.2, 0.2, n) for n in N]
+    e = list(np.exp(-2j * np.pi * np.array([0.1, 0.2, 0.3])))
+    bl = [True] * 3
+    H, ref = np.zeros_like(E), np.zeros_like(E)
+    CO.apply_curl(H, E, "=", [True] * 3, d1, bl, e)
+    CO.apply_curl(ref, H, "=", [False] * 3, d2, bl, e)
+    k0, k1 = rank * nl[2], (rank + 1) * nl[2]
+    arena = PeerArena(3 * 3 * nl[0] * nl[1] * nl[2] * 16 + 4096) if world > 1 else None
+    sync = "flags" if arena is not None else "barrier"
+    c1 = SlabCurl(S.SGC_C128, nl, [True] * 3, [d1[0], d1[1], d1[2][k0:k1]], bl, e, rank, world, arena=arena, sync=sync)
+    c2 = SlabCurl(S.SGC_C128, nl, [False] * 3, [d2[0], d2[1], d2[2][k0:k1]], bl, e, rank, world, arena=arena, sync=sync)
+    loc = S.DeviceArray.from_numpy(np.asfortranarray(E[:, :, k0:k1, :]))
+    if arena is not None:
+        A, B, Cc = (arena.array(nl + (3,)) for _ in range(3))
+        A.t.copy_(loc.t)
+    else:
+        A, B, Cc = loc, S.DeviceArray.zeros(nl + (3,)), S.DeviceArray.zeros(nl + (3,))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    for _ in range(2):  # twice: the second pass overwrites planes the neighbours read in the first (WAR ordering)
+        c1.apply(B, A, "=")
+        c2.apply(Cc, B, "=")
+    torch.cuda.synchronize()
+    err, nd = ulp_report(Cc.numpy(), ref[:, :, k0:k1, :])
+    t = torch.tensor([err], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        c1 = c2 = None
+        arena.close()
+    return {"grid": f"{N[0]}x{N[1]}x{N[2]} all-Bloch with phases, z ring over {world} rank(s)", "max_ulp": float(t.item()),
+            "ok": bool(float(t.item()) <= 4.0)}
 
 
 def main():
@@ -178,17 +438,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--graph", default="off", choices=["on", "off"])
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the step from a CUDA graph (auto: for N > 1 with in-kernel synchronisation)")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"])
-    ap.add_argument("--sync", default="barrier", choices=["flags", "barrier"],
+    ap.add_argument("--sync", default="flags", choices=["flags", "barrier"],
                     help="peer-memory halos: neighbour flags inside the stencil kernel, or a barrier kernel before every apply")
-    ap.add_argument("--slab", default="256,256,256", help="per-GPU slab Nx,Ny,Nz (default: BASELINE configs[1]; 1024,1024,128 = configs[4] at 8 GPUs)")
+    ap.add_argument("--slab", default="256,256,256", help="per-GPU slab Nx,Ny,Nz (default: BASELINE configs[1])")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the BASELINE configs[4] leg (1024x1024x128 per GPU)")
+    ap.add_argument("--no-parity", action="store_true", help="side experiments only: skip the oracle comparison")
     ap.add_argument("--no-assembly", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="side experiments only: skip the host-array leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--wc-input", action="store_true", help="experiment: write-combined pinned input buffer for the host-array leg")
     ap.add_argument("--e2e-chunks", type=int, default=16, help="z-chunks of the host-array pipeline")
-    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] (2-D operators) and fused curl-of-curl side measurements")
+    ap.add_argument("--no-extras", action="store_true", help="skip the BASELINE configs[2] (2-D operators) and other side measurements")
     ap.add_argument("--serial-e2e", action="store_true", help="N > 1: H2D, step, D2H without the chunked pipeline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -211,7 +473,6 @@ def main():
     import torch
     import torch.distributed as dist
     import sgc_b200 as S
-    from sgc_b200.slab import SlabCurl
 
     assert torch.cuda.is_available(), "bench.py needs a GPU: the product path has no CPU fallback"
     torch.cuda.set_device(local_rank)
@@ -222,115 +483,27 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    M = NLOCAL[0] * NLOCAL[1] * NLOCAL[2]
-    nz_total = NLOCAL[2] * world
-    dprim, ddual = build_inputs(nz_total)
-    k0, k1 = rank * NLOCAL[2], (rank + 1) * NLOCAL[2]
-    bl, e = [False] * 3, [1.0] * 3
-    # E -> H: forward differences with ∆l⁻¹ at dual points; H -> E': backward, primal points.
-    # N > 1: fields live in symmetric (peer-mapped) memory and the fused kernel reads its one-plane
-    # halo straight from the neighbour over NVLink; NCCL send/recv is the fallback transport.
-    arena, halo = None, "none"
-    if world > 1 and args.halo == "peer":
-        try:
-            from sgc_b200.slab import PeerArena
-            arena, halo = PeerArena(3 * 3 * M * 16 + 4096), "peer-memory loads inside the stencil kernel (symmetric memory, NVLink)"
-        except Exception as ex:
-            sys.stderr.write(f"[bench] symmetric memory unavailable ({type(ex).__name__}: {str(ex)[:120]}); using NCCL halos\n")
-    if world > 1 and arena is None:
-        halo = "NCCL send/recv on a side stream, overlapped with the interior planes"
-    sync = args.sync if arena is not None else "barrier"
-    if arena is not None and sync == "flags":
-        halo += "; neighbour synchronisation inside the kernel (flags over NVLink), no barrier kernel"
-    c_dual = SlabCurl(S.SGC_C128, NLOCAL, [True] * 3, [ddual[0], ddual[1], ddual[2][k0:k1]], bl, e, rank, world, arena=arena, sync=sync)
-    c_prim = SlabCurl(S.SGC_C128, NLOCAL, [False] * 3, [dprim[0], dprim[1], dprim[2][k0:k1]], bl, e, rank, world, arena=arena, sync=sync)
+    leg = Leg(S, torch, dist, NLOCAL, rank, world, args)
+    M = leg.M
+    E, H, E2, c_dual, c_prim, arena = leg.E, leg.H, leg.E2, leg.c_dual, leg.c_prim, leg.arena
 
-    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
-    def rnd():
-        return torch.complex(torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1,
-                             torch.rand(3 * M, generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
-    if arena is not None:
-        E, H, E2 = (arena.array(NLOCAL + (3,)) for _ in range(3))
-        E.t.copy_(rnd()); H.t.zero_(); E2.t.zero_()
-    else:
-        E = S.DeviceArray(rnd(), NLOCAL + (3,))
-        H = S.DeviceArray.zeros(NLOCAL + (3,))
-        E2 = S.DeviceArray.zeros(NLOCAL + (3,))
+    # ---- parity first: the timed configuration against the oracle, on every rank ---------------------------------
+    parity = None
+    if not args.no_parity:
+        parity = leg.parity()
+        parity["bloch_wrap_case"] = small_bloch_parity(S, torch, dist, rank, world)
+        parity["ok"] = bool(parity["ok"] and parity["bloch_wrap_case"]["ok"])
 
-    def step():
-        c_dual.apply(H, E, "=")
-        c_prim.apply(E2, H, "=")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    # The step is launch-bound on the host for N > 1 (kernels + NCCL p2p + stream joins per curl), so
-    # it is captured once into a CUDA graph and replayed: streams and graphs instead of host work.
-    graph, launches_per_step, run_step = None, None, step
-    if args.graph == "on" and world == 1:  # torch's NCCL p2p ops hang under capture (measured): N = 1 only
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                g = torch.cuda.CUDAGraph()
-                l0 = S.launch_count()
-                with torch.cuda.graph(g, stream=side):
-                    step()
-                launches_per_step = S.launch_count() - l0
-            torch.cuda.current_stream().wait_stream(side)
-            g.replay()
-            torch.cuda.synchronize()
-            graph, run_step = g, g.replay
-        except Exception as ex:  # capture unsupported for some op: stay eager
-            sys.stderr.write(f"[bench] CUDA-graph capture failed ({type(ex).__name__}: {str(ex)[:120]}); running eagerly\n")
-            graph, run_step = None, step
-            torch.cuda.synchronize()
-    ok_flags = torch.tensor([1 if graph is not None else 0], device="cuda")
-    if world > 1:  # all ranks must take the same path (a replay contains the NCCL ops)
-        dist.all_reduce(ok_flags, op=dist.ReduceOp.MIN)
-        if int(ok_flags.item()) == 0:
-            graph, run_step = None, step
-    barrier()
-    launches0 = S.launch_count()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    t_host0 = time.perf_counter()
-    for _ in range(args.steps):
-        run_step()
-    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / args.steps  # host time to enqueue one step
-    ev1.record()
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.result()
-    launches = (launches_per_step * args.steps) if graph is not None else (S.launch_count() - launches0)
-    if world > 1:
-        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = 2 * M * world / (ms_step * 1e-3) / 1e9  # Gcell-updates/s, whole job
+    use_graph = args.graph == "on" or (args.graph == "auto" and world > 1 and arena is not None and leg.sync == "flags")
+    tm = leg.time(args.steps, args.warmup, use_graph, local_rank)
+    ms_step, value = tm["ms_step"], tm["value"]
 
     # ---- end-to-end: pinned host arrays → H2D → two curls → D2H, every step ----------------------
     nbytes = 3 * M * 16
     e2e_val, e2e_s, e2e_steps, e2e_mode = None, 0.0, 1, "skipped (--no-e2e)"
     if not args.no_e2e:
         c_dual.sync = c_prim.sync = "barrier"  # host copies touch the fields between applies: full barriers
-        from sgc_b200._lib import lib as _l, check as _c
-        import ctypes as _C
-        if args.wc_input:  # write-combined pinned input (the host only writes it, the GPU reads it)
-            hp = _C.c_void_p()
-            _c(_l.sgc_malloc_host_wc(_C.byref(hp), nbytes))
-            buf = (_C.c_double * (6 * M)).from_address(hp.value)
-            E_host = torch.view_as_complex(torch.from_numpy(np.ctypeslib.as_array(buf)).view(-1, 2))
-        else:
-            E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
+        E_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
         E_host.copy_(E.t)
         Out_host = torch.empty(3 * M, dtype=torch.complex128).pin_memory()
         from sgc_b200._lib import lib, check
@@ -339,15 +512,15 @@ def main():
 
         def e2e_step_serial():
             check(lib.sgc_memcpy_h2d(C.c_void_p(E.ptr), C.c_void_p(E_host.data_ptr()), nbytes, C.c_void_p(st.cuda_stream)))
-            step()
+            leg.step()
             check(lib.sgc_memcpy_d2h(C.c_void_p(Out_host.data_ptr()), C.c_void_p(E2.ptr), nbytes, C.c_void_p(st.cuda_stream)))
             check(lib.sgc_stream_sync(C.c_void_p(st.cuda_stream)))
 
+        leg.resync()
         e2e_step, e2e_mode = e2e_step_serial, "serial: H2D, 2 curls, D2H"
         if world == 1:  # z-chunked duplex pipeline (copies in, kernels and copies out overlap)
             from sgc_b200.hostpipe import HostCurlCurl
             pipe = HostCurlCurl(c_dual.backend.op, c_prim.backend.op, NLOCAL, nchunks=args.e2e_chunks)
-            ref_out = None
             e2e_step_serial()
             ref_out = Out_host.clone()
             Out_host.zero_()
@@ -372,29 +545,18 @@ def main():
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(2):
             e2e_step()
-        barrier()
+        leg.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             e2e_step()
-        barrier()
+        leg.barrier()
         e2e_s = time.perf_counter() - t0
         if world > 1:
             t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e_val = 2 * M * world * e2e_steps / e2e_s / 1e9
-
-    # BASELINE configs[3] at N > 1: the 512^3 create_curl row-partitioned into per-GPU CSC blocks
-    asm_part = None
-    if world > 1 and not args.no_assembly:
         E_host = Out_host = None
-        asm_part = bench_assembly_partitioned(S, torch, dist, rank, world)
-
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
 
     peaks = {}
     try:
@@ -402,6 +564,47 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    other = None
+    if world == 1 and not args.no_extras and rank == 0:
+        other = bench_other_configs(S, torch, peak, c_dual.backend.op, c_prim.backend.op, E, E2, ms_step)
+    halo_txt, main_sync = leg.halo, leg.sync
+    E = H = E2 = c_dual = c_prim = arena = None
+    leg.close()
+
+    # ---- BASELINE configs[4]: the 1024^3 grid's per-GPU slab (1024x1024x128), same step, no host leg --------------
+    cfg5 = None
+    if not args.no_cfg5 and NLOCAL == (256, 256, 256):
+        try:
+            leg5 = Leg(S, torch, dist, CFG5, rank, world, args, seed_shift=100)
+            nz5 = CFG5[2]
+            p5 = None if args.no_parity else leg5.parity([(0, 3), (nz5 // 2 - 2, nz5 // 2 + 2), (nz5 - 3, nz5)])
+            use_graph5 = args.graph == "on" or (args.graph == "auto" and world > 1 and leg5.arena is not None and leg5.sync == "flags")
+            t5 = leg5.time(max(5, min(args.steps, 20)), 3, use_graph5, local_rank)
+            k5 = t5["ms_step"] / 2
+            a5 = ALG_BYTES_PER_CELL * leg5.M / (k5 * 1e-3) / 1e9
+            cfg5 = {"workload": f"BASELINE configs[4]: {CFG5[0]}x{CFG5[1]}x{CFG5[2] * world} ComplexF64 curl-of-curl, {CFG5[0]}x{CFG5[1]}x{CFG5[2]} slab per GPU",
+                    "value": t5["value"], "unit": "Gcell/s", "ms_per_step": t5["ms_step"], "per_rank_ms": t5["per_rank_ms"],
+                    "per_gpu_gbs": a5, "per_gpu_frac": a5 / peak, "cuda_graph": t5["graph"], "parity": p5}
+            if p5 is not None and parity is not None:
+                parity["ok"] = bool(parity["ok"] and p5["ok"])
+            leg5.close()
+        except Exception as ex:
+            cfg5 = {"error": f"{type(ex).__name__}: {str(ex)[:200]}"}
+
+    # BASELINE configs[3] at N > 1: the 512^3 create_curl partitioned into per-GPU CSC blocks
+    asm_part = None
+    if world > 1 and not args.no_assembly:
+        asm_part = bench_assembly_partitioned(S, torch, dist, rank, world)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        if parity is not None and not parity["ok"]:
+            sys.exit(1)
+        return
+
     kernel_ms = ms_step / 2  # the step is exactly two launches of the fused curl kernel (+ halo planes for N>1)
     achieved = ALG_BYTES_PER_CELL * M / (kernel_ms * 1e-3) / 1e9
     out = {
@@ -413,24 +616,31 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "fallback 6650 (of fallback)",
                      "frac_of_nominal_8TBs": achieved / 8000.0,
                      "algorithmic_bytes_per_launch": ALG_BYTES_PER_CELL * M},
-        "clocks": clocks,
+        "clocks": tm["clocks"],
         "e2e": {"value": e2e_val, "unit": "Gcell/s", "h2d_bytes_per_step": nbytes if e2e_val else 0, "d2h_bytes_per_step": nbytes if e2e_val else 0,
                 "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps, "mode": e2e_mode},
-        "gpu_launches": int(launches),
-        "cuda_graph": graph is not None,
-        "halo_transport": halo,
-        "host_enqueue_ms_per_step": host_enqueue_ms,
+        "gpu_launches": tm["launches"],
+        "cuda_graph": tm["graph"],
+        "per_rank_ms": tm["per_rank_ms"],
+        "halo_transport": halo_txt,
+        "host_enqueue_ms_per_step": tm["host_enqueue_ms"],
     }
     tr = os.path.join(ROOT, "profiles", "curl3_traffic.json")
-    if os.path.exists(tr) and NLOCAL == (256, 256, 256):  # the capture is of the 256^3 launch
+    if world == 1 and os.path.exists(tr) and NLOCAL == (256, 256, 256):  # the ncu capture is of the 1-GPU 256^3 launch
         try:
             out["roofline"]["traffic"] = json.load(open(tr)).get("dram_bytes_per_launch")
         except Exception:
             pass
-
+    # (order: the long side measurements first, the headline's companions last — a tail of the line keeps them)
+    if other is not None:
+        out["other_configs"] = other
+    if world == 1 and not args.no_cpu_baseline:
+        dprim, ddual = build_inputs(NLOCAL[2])
+        rate, threads, sample = cpu_reference_rate(dprim, ddual, NLOCAL[2], args.cpu_seconds)
+        out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
     if world == 1 and not args.no_assembly:
-        out["assembly"] = bench_assembly(S, torch, peak)
         out["assembly_c128"] = bench_assembly(S, torch, peak, cplx=True)
+        out["assembly"] = bench_assembly(S, torch, peak)
         if not args.no_cpu_baseline and "error" not in out["assembly"]:
             # the reference's assembly algorithm (create_∂info temporaries → COO → serial counting-sort `sparse` →
             # `dropzeros!`; C port, single thread like the stdlib) on a 128³ sample of the same matrix family
@@ -442,14 +652,11 @@ def main():
                                                    "sample": f"create_curl {n}^3 Float64 all-Bloch ({nnz_cpu} nnz) in {dt:.2f} s"}
             except Exception as ex:
                 out["assembly"]["cpu_baseline"] = {"error": str(ex)[:120]}
-    if world == 1 and not args.no_extras:
-        E_host = Out_host = None  # release the pinned staging arrays
-        out["other_configs"] = bench_other_configs(S, torch, peak, c_dual.backend.op, c_prim.backend.op, E, E2, ms_step)
     if world > 1 and not args.no_assembly:
         out["assembly"] = asm_part
-    if world == 1 and not args.no_cpu_baseline:
-        rate, threads, sample = cpu_reference_rate(dprim, ddual, NLOCAL[2], args.cpu_seconds)
-        out["cpu_baseline"] = {"value": rate, "unit": "Gcell/s", "cores": threads, "kind": "port", "sample": sample}
+    if cfg5 is not None:
+        out["cfg5"] = cfg5
+    out["parity"] = parity
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(out), flush=True)
@@ -457,6 +664,8 @@ def main():
         os.dup2(2, 1)
         dist.barrier()
         dist.destroy_process_group()
+    if parity is not None and not parity["ok"]:
+        sys.exit(1)
 
 
 def bench_assembly(S, torch, peak, cplx=False):
@@ -580,25 +789,32 @@ def _time(torch, fn, iters=10, warm=3):
 
 
 def bench_other_configs(S, torch, peak, c_dual, c_prim, E, E2, ms_two_curls):
-    """Side measurements (not the headline): the fused curl-of-curl on the headline grid, the 3-D
-    divergence / gradient, and BASELINE.json configs[2] — 2-D 8192² Float64 ∂ / m̂ / TE / TM operators
-    with PEC/PMC (symmetric) boundaries.  GB/s are ALGORITHMIC bytes / time."""
+    """Side measurements (not the headline): the fused curl-of-curl on the headline grid, 3-D divergence / gradient /
+    mean, BASELINE.json configs[2] — 2-D 8192² Float64 ∂ / m̂ / TE / TM operators with PEC/PMC (symmetric)
+    boundaries — and the other create_* assemblies.  `frac` = ALGORITHMIC bytes / time / HBM peak."""
     res = {}
+    r4 = lambda x: round(float(x), 4)
     try:
         M = NLOCAL[0] * NLOCAL[1] * NLOCAL[2]
         ms = _time(torch, lambda: c_prim.apply_after(c_dual, E2, E, "="))
         res["curlcurl_fused"] = {"what": "E' = C_prim(C_dual E) in ONE kernel, H kept in shared memory (bit-identical to the two launches)",
-                                 "ms": ms, "ms_two_launches": ms_two_curls, "gcell_updates_per_s": 2 * M / ms / 1e6,
-                                 "gbs_of_96B_per_cell": 96 * M / ms / 1e6, "frac": 96 * M / ms / 1e6 / peak}
+                                 "ms": r4(ms), "ms_two_launches": r4(ms_two_curls), "gcell_updates_per_s": r4(2 * M / ms / 1e6),
+                                 "frac_of_96B_per_cell": r4(96 * M / ms / 1e6 / peak)}
         N3 = NLOCAL
         rng = np.random.default_rng(3)
         d3 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for n in N3]
         g = S.DeviceArray.zeros(N3)
         dv = S.Operator.divg(S.SGC_C128, N3, [True] * 3, d3, [False] * 3, [1.0] * 3)
         gr = S.Operator.grad(S.SGC_C128, N3, [False] * 3, d3, [False] * 3, [1.0] * 3)
-        for name, fn in (("divg_3d_c128", lambda: dv.apply(g, E, "=")), ("grad_3d_c128", lambda: gr.apply(E2, g, "="))):
+        mn = S.Operator.mean(S.SGC_C128, N3, [True] * 3, None, None, [False] * 3, [1.0] * 3)
+        mw = S.Operator.mean(S.SGC_C128, N3, [False] * 3, d3, d3, [False] * 3, [1.0] * 3)
+        three_d = {}
+        for name, fn, B in (("divg", lambda: dv.apply(g, E, "="), 64), ("grad", lambda: gr.apply(E2, g, "="), 64),
+                            ("mean_arith", lambda: mn.apply(E2, E, "="), 96), ("mean_weighted", lambda: mw.apply(E2, E, "="), 96)):
             ms = _time(torch, fn)
-            res[name] = {"ms": ms, "launches": 1, "gbs": 64 * M / ms / 1e6, "frac": 64 * M / ms / 1e6 / peak}
+            three_d[name] = {"ms": r4(ms), "frac": r4(B * M / ms / 1e6 / peak)}
+        three_d["launches"] = {"divg": dv.launches("="), "grad": gr.launches("="), "mean": mn.launches("=")}
+        res["ops_3d_c128"] = three_d
         del g
         n = 8192
         N2, M2 = (n, n), n * n
@@ -620,9 +836,28 @@ def bench_other_configs(S, torch, peak, c_dual, c_prim, E, E2, ms_two_curls):
         two_d = {}
         for name, o, Gd, Fd, mode, B in ops:
             ms = _time(torch, lambda: o.apply(Gd, Fd, mode))
-            two_d[name] = {"ms": ms, "gcell_per_s": M2 / ms / 1e6, "gbs": B * M2 / ms / 1e6, "frac": B * M2 / ms / 1e6 / peak,
-                           "launches": o.launches(mode)}
+            two_d[name] = {"ms": r4(ms), "frac": r4(B * M2 / ms / 1e6 / peak)}
         res["ops_2d_8192_f64_pec_pmc"] = two_d
+        del F, G, F2, G1, ops
+        torch.cuda.empty_cache()
+        # the other assemblies (Float64, 384³ grid, all-Bloch with a symmetric z for the drop path), whole create_* call
+        na = 384
+        Na = (na, na, na)
+        da = [rng.uniform(0.5, 1.5, na) for _ in range(3)]
+        asm = {}
+        cases = (("create_partial", lambda: S.create_partial(3, True, Na, da[2], True)),
+                 ("create_mhat", lambda: S.create_mhat(2, False, Na, da[1], da[1], False)),
+                 ("create_mean", lambda: S.create_mean([True, False, True], da, da, [True, True, False])),
+                 ("create_divg", lambda: S.create_divg([True] * 3, da, [True, True, False])),
+                 ("create_grad", lambda: S.create_grad([False] * 3, da, [True, True, False])))
+        for name, fn in cases:
+            A = fn()
+            nnz, ncol = A.nnz, A.n
+            del A
+            ms = _time(torch, fn, iters=5, warm=1)
+            alg = nnz * 16 + (ncol + 1) * 8
+            asm[name] = {"ms": r4(ms), "gnnz_per_s": r4(nnz / ms / 1e6), "frac": r4(alg / ms / 1e6 / peak)}
+        res["assembly_others_384_f64"] = asm
     except Exception as ex:
         res["error"] = str(ex)[:200]
     return res

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define SGC_ABI_VERSION 1
+#define SGC_ABI_VERSION 2
 
 /* status codes */
 #define SGC_OK 0
@@ -186,22 +186,61 @@ int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int ndim, cons
                    int coef_complex, const int *isbloch, const double *e, const double *alpha,
                    void *stream);
 
-/* Neighbour synchronisation folded into the fused 3-D curl kernel (z-slabs in peer-mapped memory):
- * instead of a barrier kernel before every apply, the CTAs that touch the first (last) plane of
- * the slab wait (acquire loads) until the lower (upper) neighbour has published `epoch - 1`, and
- * per side the last boundary CTA to finish publishes `epoch` into that neighbour's memory
- * (release store over NVLink) — interior CTAs neither wait nor take part.  wait_lo / wait_hi: DEVICE pointers (this rank's memory) to the
- * Int64 flags the lower / upper neighbour writes (NULL: no neighbour on that side); post_lo /
- * post_hi: PEER pointers to the matching flags in the neighbours' memory; counter: two device uint32
- * (lower / upper side tickets), zero-initialised, shared by the operators of a rank.  All ranks must issue the same sequence of
- * synchronised applies with epoch = 1, 2, 3, ...; flags start at 0 and the inputs of the first
- * apply must be complete on all ranks (one ordinary barrier).  z_reverse: walk the z-chunks
- * top-down; neighbouring ranks should alternate (rank parity), so that the chunks a rank runs
- * FIRST face the chunks its neighbour ran first in the previous apply and never wait. */
-int sgc_op_set_peer_sync(sgc_op *op, const void *wait_lo, const void *wait_hi, void *post_lo, void *post_hi,
-                         void *counter, int z_reverse);
+/* ---------------------------------------------------------------------------------------- */
+/* Multi-GPU context: z-slabs of one grid on the GPUs of one node.       */
+/* apply_curl! (matrixfree/differential/curl.jl:52-63) and apply_∂! (partial.jl:33-43) on a  */
+/* slab need ONE plane from ONE z-neighbour; the fused kernel loads it straight from that     */
+/* neighbour's memory over NVLink (`ghost` pointers of sgc_op_apply_range), so all the        */
+/* library has to provide is peer-mapped memory and ordering between the ranks' kernels.      */
+/* No torch, no NCCL: plain CUDA IPC (one process per GPU) or peer access (one process).      */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct sgc_comm sgc_comm;
+#define SGC_IPC_HANDLE_BYTES 64
+
+/* One process per GPU: create the context of `rank` on the CURRENT device, fetch the handle of its control
+ * block, exchange the handles between the processes (any transport: 64 bytes per rank, rank-major), connect. */
+int sgc_comm_init(sgc_comm **comm, int world, int rank);
+int sgc_comm_handle(sgc_comm *comm, void *handle_out /* SGC_IPC_HANDLE_BYTES */);
+int sgc_comm_connect(sgc_comm *comm, const void *handles /* world x SGC_IPC_HANDLE_BYTES */);
+/* Same, for control blocks somebody else has peer-mapped already (e.g. symmetric-memory allocators):
+ * my_ctrl / peer_ctrl[r] point to sgc_comm_ctrl_bytes(world) bytes each; my_ctrl is zeroed. */
+int sgc_comm_connect_ptrs(sgc_comm *comm, void *my_ctrl, void *const *peer_ctrl);
+int sgc_comm_ctrl_bytes(int world);
+/* One process driving `ngpus` devices (0..ngpus-1): enables peer access between all pairs and returns one
+ * connected context per device in comms[0..ngpus-1]; afterwards every sgc_peer_alloc / sgc_malloc pointer is
+ * valid on every device and sgc_peer_open is not needed. */
+int sgc_comm_init_local(sgc_comm **comms, int ngpus);
+int sgc_comm_rank(const sgc_comm *comm, int *rank, int *world);
+int sgc_comm_destroy(sgc_comm *comm);
+
+/* Peer-mappable device memory on this context's device (cudaMalloc), with its IPC handle (handle_out may be
+ * NULL).  sgc_peer_open maps a neighbour's allocation into this process and returns the address this rank's
+ * kernels use for it (the base of the neighbour's allocation); sgc_peer_close unmaps it. */
+int sgc_peer_alloc(sgc_comm *comm, size_t bytes, void **dptr, void *handle_out /* SGC_IPC_HANDLE_BYTES */);
+int sgc_peer_open(sgc_comm *comm, const void *handle, void **peer_dptr);
+int sgc_peer_close(sgc_comm *comm, void *peer_dptr);
+int sgc_peer_free(sgc_comm *comm, void *dptr);
+
+/* Device-side barrier of all ranks, queued on `stream` (one small kernel: every rank writes its arrival into
+ * every peer's control block and waits for theirs).  Everything queued before it on any rank is visible to
+ * everything queued after it on every rank.  All ranks must call it the same number of times.  Graph-capturable. */
+int sgc_peer_barrier(sgc_comm *comm, void *stream);
+/* Synchronised applies finished by this rank so far (reads the control block; synchronises `stream`). */
+int sgc_comm_epoch(sgc_comm *comm, int64_t *epoch, void *stream);
+
+/* Neighbour synchronisation folded into the fused 3-D curl kernel — no barrier kernel between applies.
+ * sgc_op_attach_comm names the ranks that own the slab below / above this one (-1: none; for a Bloch z
+ * boundary the ring wraps).  sgc_op_apply_synced then runs a whole-slab apply in which only the CTAs that
+ * touch the first (last) plane take part: they are scheduled LAST, wait until the lower (upper) neighbour has
+ * finished the boundary CTAs of its previous synchronised apply, and per side the last one to finish
+ * publishes this rank's new count into that neighbour's control block over NVLink.  Interior CTAs neither
+ * wait nor count.  The count lives in device memory, so the call sequence can be captured in a CUDA graph
+ * and replayed.  Contract: all ranks issue the same sequence of synchronised applies on peer-mapped fields,
+ * nothing else modifies those fields in between, and the inputs of the first apply are complete on all
+ * ranks (one sgc_peer_barrier).  After anything else has touched the fields: sgc_peer_barrier again. */
+int sgc_op_attach_comm(sgc_op *op, sgc_comm *comm, int lo_rank, int hi_rank);
 int sgc_op_apply_synced(const sgc_op *op, void *G, const void *F, int opmode, const void *const *ghost,
-                        int64_t epoch, void *stream);
+                        void *stream);
 
 /* Fused curl-of-curl  G OP C2(C1 F)  in one pass over memory: the intermediate field
  * H = C1 F stays in shared memory (96 instead of 192 bytes per ComplexF64 cell).  Bit-identical

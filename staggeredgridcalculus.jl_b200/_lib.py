@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsgc_b200.so")
 SGC_OK, SGC_ERR_INVALID, SGC_ERR_CUDA, SGC_ERR_INEXACT, SGC_ERR_NOMEM = 0, 1, 2, 3, 4
 SGC_F64, SGC_C128 = 0, 1
 SGC_OP_SET, SGC_OP_ADD = 0, 1
+SGC_IPC_HANDLE_BYTES = 64
 
 
 class SgcError(RuntimeError):
@@ -87,8 +88,22 @@ _PROTOS = {
                                  intp, dblp, dblp, C.c_void_p]),
     "sgc_apply_mean": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, i64p, intp, vpp, vpp,
                                  C.c_int, intp, dblp, dblp, C.c_void_p]),
-    "sgc_op_set_peer_sync": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
-    "sgc_op_apply_synced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, C.c_int64, C.c_void_p]),
+    "sgc_comm_init": (C.c_int, [vpp, C.c_int, C.c_int]),
+    "sgc_comm_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgc_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgc_comm_connect_ptrs": (C.c_int, [C.c_void_p, C.c_void_p, vpp]),
+    "sgc_comm_ctrl_bytes": (C.c_int, [C.c_int]),
+    "sgc_comm_init_local": (C.c_int, [vpp, C.c_int]),
+    "sgc_comm_rank": (C.c_int, [C.c_void_p, intp, intp]),
+    "sgc_comm_destroy": (C.c_int, [C.c_void_p]),
+    "sgc_peer_alloc": (C.c_int, [C.c_void_p, C.c_size_t, vpp, C.c_void_p]),
+    "sgc_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, vpp]),
+    "sgc_peer_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgc_peer_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sgc_comm_epoch": (C.c_int, [C.c_void_p, i64p, C.c_void_p]),
+    "sgc_op_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "sgc_op_apply_synced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, C.c_void_p]),
     "sgc_op_apply_curlcurl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "sgc_op_apply_curlcurl_range": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, vpp,
                                               C.c_int64, C.c_int64, C.c_void_p]),

@@ -41,13 +41,13 @@ int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghos
     }
     p.Nx = (int)op->N[0]; p.Ny = (int)op->N[1]; p.Nz = (int)op->N[2];
     p.k_begin = (int)k_begin; p.k_end = (int)k_end;
-    if (op->sync_epoch > 0) {
-        if ((op->variant & 0xF) != 0 || k_begin != 0 || k_end != op->N[2] || !op->sync_counter)
-            return sgc_fail(SGC_ERR_INVALID, "synchronised apply needs the default kernel, the whole slab and sgc_op_set_peer_sync");
-        for (int sd = 0; sd < 2; ++sd) { p.sync_wait[sd] = op->sync_wait[sd]; p.sync_post[sd] = op->sync_post[sd]; }
-        p.sync_epoch = op->sync_epoch;
-        p.sync_counter = op->sync_counter;
-        p.z_reverse = op->sync_z_reverse;
+    if (op->sync_on) {
+        if ((op->variant & 0xF) != 0 || k_begin != 0 || k_end != op->N[2] || !op->sync_ctrl)
+            return sgc_fail(SGC_ERR_INVALID, "synchronised apply needs the default kernel, the whole slab and sgc_op_attach_comm");
+        if (op->sync_side[0] || op->sync_side[1]) {
+            p.sync_ctrl = op->sync_ctrl;
+            for (int sd = 0; sd < 2; ++sd) { p.sync_post[sd] = op->sync_post[sd]; p.sync_side[sd] = op->sync_side[sd]; }
+        }
     }
 
     const int kernel_variant = op->variant & 0xF;
@@ -91,11 +91,8 @@ template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, boo
 static int launch_curl3p_one(const CurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = (size_t)S * 3 * (TY + 1) * (TX + 1) * sizeof(T);
     auto kern = k_curl3p<T, C, ADD, TX, TY, S, MINB, XSHFL>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_devices{0};  // per instantiation: the devices the attribute has been set on
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
     kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
     return SGC_OK;
 }
@@ -145,11 +142,8 @@ static int launch_divgrad_one(const CurlParams<T, C> &p, dim3 grid, cudaStream_t
     constexpr int TX = 32, TY = 4, S = 6, MINB = 4;
     constexpr size_t smem = (size_t)S * 3 * (TY + 1) * (TX + 1) * sizeof(T);
     auto kern = k_curl3p<T, C, ADD, TX, TY, S, MINB, true, MODE>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_devices{0};  // per instantiation: the devices the attribute has been set on
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
     kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
     return SGC_OK;
 }

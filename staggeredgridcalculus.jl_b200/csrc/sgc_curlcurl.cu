@@ -14,11 +14,8 @@ template <typename T, typename C, bool ADD, int TX, int TY, int SE, int MINB>
 int launch_cc_one(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)SE * 3 * (TX + 2) * (TY + 2) + (size_t)3 * 3 * (TX + 1) * (TY + 1)) * sizeof(T);
     auto kern = k_curlcurl3<T, C, ADD, TX, TY, SE, MINB>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_devices{0};  // per instantiation: the devices the attribute has been set on
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
     kern<<<grid, dim3(TX, TY, 1), smem, st>>>(p);
     return SGC_OK;
 }
@@ -39,11 +36,8 @@ template <typename T, typename C, bool ADD, int TY, int SE, bool FZ1, bool FZ2>
 int launch_ccw_one(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)SE * 3 * 34 * (TY + 2) + (size_t)3 * 3 * 33 * (TY + 1)) * sizeof(T);
     auto kern = k_curlcurl3w<T, C, ADD, TY, SE, FZ1, FZ2>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
+    static std::atomic<uint64_t> attr_devices{0};  // per instantiation: the devices the attribute has been set on
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
     kern<<<grid, dim3(32, TY + 1, 1), smem, st>>>(p);
     return SGC_OK;
 }

@@ -120,12 +120,11 @@ struct sgc_op {
     size_t fused_off[3] = {0, 0, 0};
     int fused_pat = -1;           // PAT_* when the term list is one of the one-launch compositions
     int lo_iface = 0, hi_iface = 0;
-    // neighbour synchronisation folded into the fused curl kernel (sgc_op_set_peer_sync)
-    const long long *sync_wait[2] = {nullptr, nullptr};
-    long long *sync_post[2] = {nullptr, nullptr};
-    unsigned *sync_counter = nullptr;
-    int sync_z_reverse = 0;
-    mutable long long sync_epoch = 0;                // epoch of the apply being launched (0: plain apply)
+    // neighbour synchronisation folded into the fused curl kernel (sgc_op_attach_comm, sgc_comm.cu)
+    long long *sync_ctrl = nullptr;                  // this rank's control block
+    long long *sync_post[2] = {nullptr, nullptr};    // the neighbours' flag slots (peer addresses)
+    int sync_side[2] = {0, 0};
+    mutable bool sync_on = false;                    // set around the launch by sgc_op_apply_synced
     // weighted means on a slab: ∆w of the neighbour's plane below / above (sgc_op_set_slab_weights)
     bool has_slab_w = false;
     HV slab_w[2] = {{1.0, 0.0, false}, {1.0, 0.0, false}};
@@ -163,5 +162,19 @@ template <typename T, typename C>
 int sgc_launch_divgrad3(const sgc_op *op, bool is_divg, T *G, const T *F, const void *const *ghost, bool add_mode,
                         int64_t k_begin, int64_t k_end, cudaStream_t st);
 int sgc_check_common(int dtype, int ndim, const int64_t *N);
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: remember, per kernel instantiation, on
+// which devices it has been set (bit d of `done`).  Lock-free; a racing second call is harmless.
+template <typename K>
+static inline cudaError_t sgc_set_dynamic_smem(K kern, size_t smem, std::atomic<uint64_t> &done) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
 #define fail sgc_fail
 #define check_launch sgc_check_launch

@@ -366,6 +366,10 @@ __global__ void __launch_bounds__(256) k_fill_zero(T *G, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // Fused full 3-D curl
 // ---------------------------------------------------------------------------------------------
+// slots of a rank's control block (int64 each; sgc_comm.cu allocates and peer-maps it)
+enum : int { SGC_CTRL_FLAG_LO = 0, SGC_CTRL_FLAG_HI = 1, SGC_CTRL_EPOCH = 2, SGC_CTRL_TICKETS = 3 /* 2 x uint32 */,
+             SGC_CTRL_SIDES_DONE = 4 /* uint32 */, SGC_CTRL_BAR_COUNT = 5, SGC_CTRL_BAR_SLOTS = 8 /* + world */ };
+
 template <typename T, typename C>
 struct CurlParams {
     const T *F[3];       // Fx, Fy, Fz  (each Nx*Ny*Nz)
@@ -379,17 +383,18 @@ struct CurlParams {
     int Nx, Ny, Nz;
     int k_begin, k_end;  // planes to produce
     int march;           // planes per CTA
-    // neighbour synchronisation folded into the kernel (z-slabs in peer memory, no barrier kernel):
-    // the CTAs that touch the first (last) plane of the slab wait until the lower (upper) neighbour's
-    // boundary CTAs of its previous apply are done (flag the neighbour wrote into MY memory ≥ epoch − 1);
-    // per side, the last boundary CTA to finish publishes `epoch` into that neighbour's memory.
-    // Interior CTAs neither wait nor count.  sync_counter: two tickets (lower, upper).  epoch == 0: off.
-    const long long *sync_wait[2];
-    long long *sync_post[2];
-    long long sync_epoch;
-    unsigned *sync_counter;
-    int z_reverse;  // walk the z-chunks top-down (ranks alternate, so that a rank's first wave never waits on the
-                    // chunks its neighbour runs last)
+    // neighbour synchronisation folded into the kernel (z-slabs in peer memory, no barrier kernel), see
+    // sgc_comm.cu: the CTAs that touch the first (last) plane of the slab wait until the lower (upper) neighbour
+    // has finished the boundary CTAs of its previous synchronised apply (the count that neighbour wrote into MY
+    // control block >= my own count of finished applies); per side, the last boundary CTA to finish publishes
+    // count + 1 into that neighbour's control block, and the last side to finish advances my own count.  The count
+    // lives in device memory (sync_ctrl[SGC_CTRL_EPOCH]), so the launch is the same every time and can be replayed
+    // from a CUDA graph.  Interior CTAs neither wait nor count.  The z-chunks are rotated by one so that the two
+    // boundary chunks are scheduled LAST: a whole kernel duration of slack against neighbour skew, and the peer
+    // loads of the ghost plane overlap the interior.  sync_ctrl == nullptr: off.
+    long long *sync_ctrl;            // this rank's control block (SGC_CTRL_* slots)
+    long long *sync_post[2];         // peer addresses: the lower neighbour's FLAG_HI slot, the upper neighbour's FLAG_LO slot
+    int sync_side[2];                // this rank has a neighbour on the lower / upper side
 };
 
 SGC_D long long ld_acquire_sys(const long long *p) {
@@ -399,6 +404,14 @@ SGC_D long long ld_acquire_sys(const long long *p) {
 }
 SGC_D void st_release_sys(long long *p, long long v) {
     asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+SGC_D long long ld_volatile_s64(const long long *p) {
+    long long v;
+    asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+SGC_D void st_volatile_s64(long long *p, long long v) {
+    asm volatile("st.volatile.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // One CTA owns a TX×TY column of cells and marches `march` planes up in z.
@@ -770,7 +783,8 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
     const C cxs = fx ? cxi : neg(cxi);
     const C cys = fy ? cyj : neg(cyj);
 
-    const int zchunk = p.z_reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
+    // synchronised applies run the two boundary chunks last (chunk order 1, 2, ..., nzc−1, 0)
+    const int zchunk = p.sync_ctrl ? ((blockIdx.z + 1 == gridDim.z) ? 0 : (int)blockIdx.z + 1) : (int)blockIdx.z;
     const int k0 = p.k_begin + zchunk * p.march;
     const int k1 = min(k0 + p.march, p.k_end);
     if (k0 >= k1) return;
@@ -778,14 +792,15 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
     const int base = fz ? k0 : k0 - 1;  // grid plane of slot 0
     const T Z = zero_of(T{});
 
-    if (p.sync_epoch > 0 && (k0 == 0 || k1 == Nz)) {
+    if (p.sync_ctrl && (k0 == 0 || k1 == Nz)) {
         // this CTA reads a neighbour's plane or overwrites a plane a neighbour may still be reading: the
         // neighbour on that side must have finished the boundary CTAs of its previous apply
         if (lin == 0) {
-            if (k0 == 0 && p.sync_wait[0])
-                while (ld_acquire_sys(p.sync_wait[0]) < p.sync_epoch - 1) __nanosleep(64);
-            if (k1 == Nz && p.sync_wait[1])
-                while (ld_acquire_sys(p.sync_wait[1]) < p.sync_epoch - 1) __nanosleep(64);
+            const long long done = ld_volatile_s64(p.sync_ctrl + SGC_CTRL_EPOCH);  // my finished applies
+            if (k0 == 0 && p.sync_side[0])
+                while (ld_acquire_sys(p.sync_ctrl + SGC_CTRL_FLAG_LO) < done) __nanosleep(64);
+            if (k1 == Nz && p.sync_side[1])
+                while (ld_acquire_sys(p.sync_ctrl + SGC_CTRL_FLAG_HI) < done) __nanosleep(64);
         }
         __syncthreads();
     }
@@ -980,22 +995,30 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
         ylo = yhi;
     }
     cp_async_wait<0>();
-    if (p.sync_epoch > 0 && (k0 == 0 || k1 == Nz)) {
-        // per side: the last boundary CTA to finish tells that neighbour that this rank's apply #epoch has
-        // written (and no longer reads) the planes at that interface; interior CTAs take no part
+    if (p.sync_ctrl && (k0 == 0 || k1 == Nz)) {
+        // per side: the last boundary CTA to finish tells that neighbour that this rank's apply has written (and
+        // no longer reads) the planes at that interface; the last side advances this rank's own count
         __syncthreads();
         if (lin == 0) {
             __threadfence();
             const unsigned side_total = gridDim.x * gridDim.y;
-            if (k0 == 0 && p.sync_post[0] && atomicAdd(p.sync_counter, 1u) == side_total - 1) {
-                p.sync_counter[0] = 0;
-                __threadfence_system();
-                st_release_sys(p.sync_post[0], p.sync_epoch);
-            }
-            if (k1 == Nz && p.sync_post[1] && atomicAdd(p.sync_counter + 1, 1u) == side_total - 1) {
-                p.sync_counter[1] = 0;
-                __threadfence_system();
-                st_release_sys(p.sync_post[1], p.sync_epoch);
+            const unsigned nsides = (unsigned)(p.sync_side[0] + p.sync_side[1]);
+            unsigned *const tickets = reinterpret_cast<unsigned *>(p.sync_ctrl + SGC_CTRL_TICKETS);
+            unsigned *const sides_done = reinterpret_cast<unsigned *>(p.sync_ctrl + SGC_CTRL_SIDES_DONE);
+            const long long done = ld_volatile_s64(p.sync_ctrl + SGC_CTRL_EPOCH);  // unchanged until all sides are through
+#pragma unroll
+            for (int sd = 0; sd < 2; ++sd) {
+                const bool mine = sd == 0 ? (k0 == 0) : (k1 == Nz);
+                if (mine && p.sync_side[sd] && atomicAdd(tickets + sd, 1u) == side_total - 1) {
+                    tickets[sd] = 0;
+                    __threadfence_system();
+                    st_release_sys(p.sync_post[sd], done + 1);
+                    if (atomicAdd(sides_done, 1u) == nsides - 1) {
+                        *sides_done = 0;
+                        __threadfence();
+                        st_volatile_s64(p.sync_ctrl + SGC_CTRL_EPOCH, done + 1);
+                    }
+                }
             }
         }
     }

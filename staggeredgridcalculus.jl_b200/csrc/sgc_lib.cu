@@ -728,29 +728,6 @@ extern "C" int sgc_op_apply_range(const sgc_op *op, void *G, const void *F, int 
     return apply_typed<cplx>(op, (cplx *)G, (const cplx *)F, opmode, ghost, k_begin, k_end, st);
 }
 
-extern "C" int sgc_op_set_peer_sync(sgc_op *op, const void *wait_lo, const void *wait_hi, void *post_lo, void *post_hi,
-                                    void *counter, int z_reverse) {
-    REQUIRE(op, "op is NULL");
-    REQUIRE(op->fused_curl, "peer synchronisation is built into the fused 3-D curl kernel only");
-    REQUIRE(counter, "counter is NULL");
-    op->sync_wait[0] = (const long long *)wait_lo; op->sync_wait[1] = (const long long *)wait_hi;
-    op->sync_post[0] = (long long *)post_lo; op->sync_post[1] = (long long *)post_hi;
-    op->sync_counter = (unsigned *)counter;
-    op->sync_z_reverse = z_reverse ? 1 : 0;
-    return SGC_OK;
-}
-
-extern "C" int sgc_op_apply_synced(const sgc_op *op, void *G, const void *F, int opmode, const void *const *ghost,
-                                   int64_t epoch, void *stream) {
-    REQUIRE(op, "op is NULL");
-    REQUIRE(epoch >= 1, "epoch must be >= 1");
-    REQUIRE(op->fused_curl && op->sync_counter, "call sgc_op_set_peer_sync on a full 3-D curl operator first");
-    op->sync_epoch = epoch;
-    int s = sgc_op_apply_range(op, G, F, opmode, ghost, 0, op->N[op->ndim - 1], stream);
-    op->sync_epoch = 0;
-    return s;
-}
-
 extern "C" int sgc_op_apply(const sgc_op *op, void *G, const void *F, int opmode, void *stream) {
     REQUIRE(op, "op is NULL");
     return sgc_op_apply_range(op, G, F, opmode, nullptr, 0, op->N[op->ndim - 1], stream);

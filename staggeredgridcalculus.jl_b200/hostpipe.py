@@ -17,6 +17,7 @@ import ctypes as C
 
 import torch
 
+from . import _lib
 from ._lib import lib, check
 from .device import DeviceArray
 from .matrixfree import Operator
@@ -47,6 +48,11 @@ def pipeline_plan(nz: int, nchunks: int, lo_iface: bool = False, hi_iface: bool 
 
 class HostCurlCurl:
     def __init__(self, curl_fwd: Operator, curl_bwd: Operator, N, nchunks=8):
+        # the plane plan below is only valid for: first curl forward in z, second backward, non-periodic z
+        f1, f2, bl = getattr(curl_fwd, "isfwd", None), getattr(curl_bwd, "isfwd", None), getattr(curl_fwd, "isbloch", None)
+        if f1 is None or f2 is None or not f1[2] or f2[2] or bl[2] or getattr(curl_bwd, "isbloch", bl)[2]:
+            raise _lib.SgcError(_lib.SGC_ERR_INVALID, "HostCurlCurl streams z-chunks for a forward-z first curl, a backward-z "
+                                "second curl and a non-periodic z boundary; use Operator.apply_host for other combinations")
         self.c1, self.c2 = curl_fwd, curl_bwd
         self.N = tuple(int(n) for n in N)
         self.plane = self.N[0] * self.N[1]

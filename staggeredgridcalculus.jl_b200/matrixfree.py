@@ -85,7 +85,9 @@ class Operator:
         check(lib.sgc_op_create_curl(C.byref(h), dtype_code, K, int64s(N), ints(isfwd), arr, cc, ints(isbloch),
                                      scalars2(e), ints(cmp_shp), len(cmp_out), ints(cmp_out), len(cmp_in),
                                      ints(cmp_in), scalar2(alpha)))
-        return cls(h, dtype_code, N, len(cmp_out), len(cmp_in), keep)
+        o = cls(h, dtype_code, N, len(cmp_out), len(cmp_in), keep)
+        o.isfwd, o.isbloch = [bool(b) for b in isfwd], [bool(b) for b in isbloch]  # (host pipelines check their plan against these)
+        return o
 
     @classmethod
     def divg(cls, dtype_code, N, isfwd, dlinv=None, isbloch=None, e=None, alpha=1.0):
@@ -153,18 +155,19 @@ class Operator:
         check(lib.sgc_op_apply_range(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr,
                                      int(k_begin), int(k_end), stream_handle(stream)))
 
-    def set_peer_sync(self, wait_lo, wait_hi, post_lo, post_hi, counter, z_reverse=False):
-        """Device / peer pointers (ints or None) of the neighbour flags, see `sgc_op_set_peer_sync`."""
-        v = lambda x: None if x is None else C.c_void_p(int(x))
-        check(lib.sgc_op_set_peer_sync(self._h, v(wait_lo), v(wait_hi), v(post_lo), v(post_hi), v(counter), int(bool(z_reverse))))
+    def attach_comm(self, comm_handle, lo_rank, hi_rank):
+        """Neighbour synchronisation inside the fused curl kernel (`sgc_op_attach_comm`): the ranks owning the slab
+        below / above this one, or None."""
+        check(lib.sgc_op_attach_comm(self._h, comm_handle, -1 if lo_rank is None else int(lo_rank),
+                                     -1 if hi_rank is None else int(hi_rank)))
 
-    def apply_synced(self, G, F, op, ghost, epoch, stream=None):
+    def apply_synced(self, G, F, op, ghost, stream=None):
         """One whole-slab apply whose neighbour synchronisation happens inside the kernel."""
         self._check_arrays(G, F)
         garr = None
         if ghost is not None:
             garr = (C.c_void_p * self.n_in)(*[None if g is None else int(g) for g in ghost])
-        check(lib.sgc_op_apply_synced(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr, int(epoch),
+        check(lib.sgc_op_apply_synced(self._h, C.c_void_p(G.ptr), C.c_void_p(F.ptr), opcode(op), garr,
                                       stream_handle(stream)))
 
     def apply_after(self, first: "Operator", G: DeviceArray, F: DeviceArray, op="=", k_begin=None, k_end=None,

@@ -32,7 +32,10 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+import ctypes as C
+
 from . import _lib
+from ._lib import lib, check
 from .device import DeviceArray
 from .matrixfree import Operator
 
@@ -104,46 +107,157 @@ class CudaBackend:
         torch.cuda.current_stream().wait_stream(self.comm_stream)
 
 
+class _RawCuda:
+    """A raw device allocation seen through `__cuda_array_interface__` (torch only wraps it; the library owns it)."""
+
+    def __init__(self, ptr, n_f64):
+        self.__cuda_array_interface__ = {"shape": (int(n_f64),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
 class PeerArena:
-    """Symmetric (peer-mapped) device memory for the fields of a slab-decomposed problem
-    (`torch.distributed._symmetric_memory`: every rank allocates the same number of bytes and can
-    address every other rank's allocation over NVLink).  Fields are carved out of one arena with
-    `array()`; all ranks must carve the same sequence so that offsets agree."""
+    """Peer-mapped device memory for the fields of a slab-decomposed problem plus the library's multi-GPU context
+    (`sgc_comm`, csrc/sgc_comm.cu).  Every rank allocates the same number of bytes with `sgc_peer_alloc`
+    (plain cudaMalloc memory + a CUDA IPC handle), the 64-byte handles travel through one `all_gather`, and each
+    rank maps the others' allocations with `sgc_peer_open` — torch.distributed is only the courier of the
+    handles.  Fields are carved out of the arena with `array()`; all ranks must carve the same sequence so that
+    offsets agree.  `backend="symm"` (or a failing IPC mapping under `"auto"`) uses
+    `torch.distributed._symmetric_memory` for the mapping instead; barrier and neighbour flags are the
+    library's either way."""
 
-    def __init__(self, nbytes, group=None):
-        import torch.distributed._symmetric_memory as symm
+    def __init__(self, nbytes, group=None, backend="auto"):
         group = group or dist.group.WORLD
+        self.group = group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
-        self.buf = symm.empty((int(nbytes) + 15) // 16 * 2, dtype=torch.float64, device=f"cuda:{torch.cuda.current_device()}")
-        self.hdl = symm.rendezvous(self.buf, group.group_name)
-        self.base = self.buf.data_ptr()
+        self.dev = torch.cuda.current_device()
+        nbytes = (int(nbytes) + 255) // 256 * 256
+        self.nbytes = nbytes
+        self.comm = C.c_void_p()
+        check(lib.sgc_comm_init(C.byref(self.comm), self.world, self.rank))
+        self.backend = None
+        if backend in ("auto", "ipc"):
+            err = self._init_ipc(nbytes)   # collective: every rank walks through the same all_gather / all_reduce
+            if err is None:
+                self.backend = "ipc"
+            elif backend == "ipc":
+                raise _lib.SgcError(_lib.SGC_ERR_CUDA, f"CUDA IPC peer mapping failed: {err}")
+            else:
+                import sys
+                sys.stderr.write(f"[sgc] CUDA IPC peer mapping unavailable ({err[:160]}); using symmetric memory for the mapping\n")
+        if self.backend is None:
+            self._init_symm(nbytes)
+            self.backend = "symm"
         self.used = 0
-        # neighbour flags for the in-kernel synchronisation: [0] written by the lower neighbour, [1] by the upper
-        # one, [2] the CTA ticket counter of this rank; `epoch` counts this rank's synchronised applies
-        self.flags = self.array((4,), np.float64)
-        self.flags.t.zero_()
-        self.epoch = 0
 
+    # ---- mappings ---------------------------------------------------------------------------------------------
+    def _all_gather_bytes(self, payload: bytes):
+        t = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(out, t, group=self.group)
+        return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+    def _all_min(self, ok: bool) -> bool:
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(int(flag.item()))
+
+    def _init_ipc(self, nbytes):
+        """Returns None on success, else a description of what failed (on ANY rank)."""
+        H = _lib.SGC_IPC_HANDLE_BYTES
+        hc, hb, base, err = (C.c_ubyte * H)(), (C.c_ubyte * H)(), C.c_void_p(), None
+        try:
+            check(lib.sgc_comm_handle(self.comm, hc))
+            check(lib.sgc_peer_alloc(self.comm, nbytes, C.byref(base), hb))
+        except Exception as ex:
+            err = f"rank {self.rank}: {ex}"
+        got = self._all_gather_bytes(bytes([0 if err is None else 1]) + bytes(hc) + bytes(hb))
+        if any(g[0] for g in got):
+            if base.value:
+                lib.sgc_free(base)
+            return err or "another rank could not export its allocation"
+        self.base = int(base.value)
+        self.peer_base = [self.base] * self.world
+        try:
+            check(lib.sgc_comm_connect(self.comm, b"".join(g[1:1 + H] for g in got)))
+            for r, g in enumerate(got):
+                if r != self.rank:
+                    pp = C.c_void_p()
+                    check(lib.sgc_peer_open(self.comm, g[1 + H:], C.byref(pp)))
+                    self.peer_base[r] = int(pp.value)
+            self.buf = torch.as_tensor(_RawCuda(self.base, nbytes // 8), device=f"cuda:{self.dev}")
+        except Exception as ex:
+            err = f"rank {self.rank}: {ex}"
+        if not self._all_min(err is None):
+            lib.sgc_comm_destroy(self.comm)
+            lib.sgc_free(base)
+            self.comm = C.c_void_p()
+            check(lib.sgc_comm_init(C.byref(self.comm), self.world, self.rank))
+            return err or "another rank could not map its neighbours"
+        self._owned = True
+        return None
+
+    def _init_symm(self, nbytes):
+        import torch.distributed._symmetric_memory as symm
+        cb = int(lib.sgc_comm_ctrl_bytes(self.world))
+        cb = (cb + 255) // 256 * 256
+        self.buf_all = symm.empty((nbytes + cb) // 8, dtype=torch.float64, device=f"cuda:{self.dev}")
+        self.hdl = symm.rendezvous(self.buf_all, self.group.group_name)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        arr = (C.c_void_p * self.world)(*ptrs)
+        check(lib.sgc_comm_connect_ptrs(self.comm, C.c_void_p(ptrs[self.rank]), arr))
+        self.buf = self.buf_all[cb // 8:]
+        self.base = self.buf.data_ptr()
+        self.peer_base = [p + cb for p in ptrs]
+        self._owned = False
+        dist.barrier(group=self.group)  # every control block is zeroed before anyone signals
+
+    # ---- carving ------------------------------------------------------------------------------------------------
     def array(self, shape, dtype=np.complex128) -> DeviceArray:
         n = int(np.prod(shape, dtype=np.int64))
         es = 16 if np.dtype(dtype) == np.complex128 else 8
-        off = (self.used + 15) // 16 * 16
-        if off + n * es > self.buf.numel() * 8:
+        off = (self.used + 255) // 256 * 256
+        if off + n * es > self.nbytes:
             raise _lib.SgcError(_lib.SGC_ERR_NOMEM, "PeerArena exhausted")
         self.used = off + n * es
         flat = self.buf[off // 8: off // 8 + n * es // 8]
         t = torch.view_as_complex(flat.view(-1, 2)) if es == 16 else flat
-        return DeviceArray(t, shape)
+        a = DeviceArray(t, shape)
+        a._arena_keepalive = self
+        return a
 
     def peer_ptr(self, arr: DeviceArray, peer: int) -> int:
         off = arr.ptr - self.base
-        if not 0 <= off < self.buf.numel() * 8:
+        if not 0 <= off < self.nbytes:
             raise _lib.SgcError(_lib.SGC_ERR_INVALID, "the field does not live in this PeerArena")
-        return int(self.hdl.buffer_ptrs[peer]) + off
+        return self.peer_base[peer] + off
 
-    def barrier(self):
-        """Device-side barrier of all ranks, ordered on the current stream."""
-        self.hdl.barrier(channel=0)
+    def barrier(self, stream=None):
+        """Device-side barrier of all ranks (`sgc_peer_barrier`), ordered on the current stream."""
+        from .device import stream_handle
+        check(lib.sgc_peer_barrier(self.comm, stream_handle(stream)))
+
+    def epoch(self) -> int:
+        from .device import stream_handle
+        v = C.c_int64()
+        check(lib.sgc_comm_epoch(self.comm, C.byref(v), stream_handle(None)))
+        return int(v.value)
+
+    def assert_same(self, value, what="slab shape"):
+        """The peer paths address the neighbour's planes with the LOCAL slab extents: all ranks must agree."""
+        vals = [None] * self.world
+        dist.all_gather_object(vals, tuple(value), group=self.group)
+        if any(v != vals[0] for v in vals):
+            raise _lib.SgcError(_lib.SGC_ERR_INVALID, f"{what} differs between ranks ({vals}): the peer-memory halo "
+                                "paths need equal slabs (pad nz to a multiple of the world size, or use the NCCL transport)")
+
+    def close(self):
+        if getattr(self, "comm", None) is not None and self.comm.value:
+            torch.cuda.synchronize()
+            base = self.base if self._owned else None
+            lib.sgc_comm_destroy(self.comm)   # closes the IPC mappings it opened
+            self.comm = C.c_void_p()
+            if base:
+                lib.sgc_free(C.c_void_p(base))
 
 
 class SlabCurl:
@@ -171,20 +285,22 @@ class SlabCurl:
         self.ghost = None
         if self.arena is None and self.plan["recv_from"] is not None:
             self.ghost = self.backend.alloc_ghost()
+        if self.arena is not None:
+            self.arena.assert_same(self.N)
 
     def _setup_flag_sync(self):
-        """Neighbour ranks along z (ring if the global z boundary is Bloch) and their flag addresses."""
-        a, r, w = self.arena, self.rank, self.world
+        """Neighbour ranks along z (ring if the global z boundary is Bloch): `sgc_op_attach_comm`."""
+        r, w = self.rank, self.world
         lo = r - 1 if r > 0 else (w - 1 if self.bloch_z and w > 1 else None)
         hi = r + 1 if r < w - 1 else (0 if self.bloch_z and w > 1 else None)
-        f = a.flags
-        wait_lo = f.ptr if lo is not None else None           # flags[0]: written by my lower neighbour
-        wait_hi = f.ptr + 8 if hi is not None else None       # flags[1]: written by my upper neighbour
-        post_lo = a.peer_ptr(f, lo) + 8 if lo is not None else None   # I am the UPPER neighbour of `lo`
-        post_hi = a.peer_ptr(f, hi) if hi is not None else None       # I am the LOWER neighbour of `hi`
-        # (z_reverse: alternating the CTA z-order by rank parity measured 2.7 % slower — left off)
-        self.backend.op.set_peer_sync(wait_lo, wait_hi, post_lo, post_hi, f.ptr + 16, z_reverse=False)
+        self.backend.op.attach_comm(self.arena.comm, lo, hi)
         self._flag_sync_ready = True
+
+    def resync(self):
+        """After anything other than synchronised applies has touched the fields (host copies, other kernels):
+        one all-rank barrier re-establishes the precondition of the in-kernel neighbour synchronisation."""
+        if self.arena is not None:
+            self.arena.barrier()
 
     def _apply_peer(self, G, F, op):
         """One fused kernel; the ghost pointers are the neighbour's planes (NVLink loads)."""
@@ -201,10 +317,10 @@ class SlabCurl:
             # the last CTA publishes this one — no barrier kernel, the interior never waits
             if not getattr(self, "_flag_sync_ready", False):
                 self._setup_flag_sync()
-            if self.arena.epoch == 0:
+            if not getattr(self.arena, "_synced_once", False):
                 self.arena.barrier()  # the inputs of the very first synchronised apply
-            self.arena.epoch += 1
-            self.backend.op.apply_synced(G, F, op, ghost, self.arena.epoch)
+                self.arena._synced_once = True
+            self.backend.op.apply_synced(G, F, op, ghost)
             return
         self.arena.barrier()  # every rank's F is complete, and nobody still reads what G overwrites
         self.backend.op.apply_range(G, F, op, 0, Nz, ghost)
@@ -268,6 +384,8 @@ class SlabCurlCurl:
             if (self.lo is not None and dz1_below is None) or (self.hi is not None and dz1_above is None):
                 raise _lib.SgcError(_lib.SGC_ERR_INVALID, "dz1_below / dz1_above are needed wherever a neighbour rank exists")
             self.c1.set_slab_coef(dz1_below if self.lo is not None else None, dz1_above if self.hi is not None else None)
+        if self.arena is not None:
+            self.arena.assert_same(self.N)
 
     def apply(self, G, F, op="="):
         if self.arena is None:
@@ -307,6 +425,8 @@ class SlabOp:
         self.plan = halo_plan(rank, world, bool(isfwd_last), bool(isbloch_last)) if isfwd_last is not None else None
         op.set_slab(lo_interface=rank > 0, hi_interface=rank < world - 1)
         self.esize = 16 if op.dtype_code == _lib.SGC_C128 else 8
+        if self.arena is not None:
+            self.arena.assert_same(op.N)
 
     def apply(self, G, F, op="="):
         N = self.op.N

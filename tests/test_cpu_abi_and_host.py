@@ -24,7 +24,7 @@ def test_library_exports_every_symbol_the_header_declares():
     missing = [s for s in declared if not hasattr(lib, s)]
     assert not missing, f"libsgc_b200.so lacks {missing}"
     assert sorted(sgc_b200._lib._PROTOS) == declared, "the ctypes binding and the header disagree"
-    assert lib.sgc_abi_version() == 1
+    assert lib.sgc_abi_version() == 2
 
 
 def test_no_cpu_fallback_product_path_fails_loudly_without_gpu():
