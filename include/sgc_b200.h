@@ -262,10 +262,27 @@ int sgc_op_apply_curlcurl_range(const sgc_op *c2, const sgc_op *c1, void *G, con
  * element each (re[,im]); NULL = 1.0.  Stored pre-multiplied by alpha like the tables. */
 int sgc_op_set_slab_coef(sgc_op *op, const double *dzinv_below, const double *dzinv_above, int coef_complex);
 
-/* Host-array convenience (strict drop-in for Julia `Array`s; PCIe-bound): copies F (and G for
- * SGC_OP_ADD) to the device, applies, copies G back, synchronises.  `G_host`/`F_host` hold
- * n_out / n_in components of prod(N) elements each. */
+/* Host-array entry points (the strict drop-in form: Julia `Array`s in host memory; PCIe-bound).  `G_host` /
+ * `F_host` hold n_out / n_in components of prod(N) elements each.  The caller's arrays are page-locked in place the
+ * first time they are seen (cudaHostRegister, cached — see sgc_host_set_registration), the input streams in
+ * z-chunks, the kernels run on each chunk's planes as soon as the planes their stencil reaches have arrived, and
+ * the result streams out on a third stream, so that H2D, compute and D2H overlap.  The call returns when G_host
+ * is complete.  sgc_op_apply_host = apply_∂! / apply_m̂! / apply_curl! / apply_divg! / apply_grad! / apply_mean!
+ * with host arrays (matrixfree/differential/partial.jl:33-43, curl.jl:52-63, …); nchunks <= 0 picks a default. */
 int sgc_op_apply_host(const sgc_op *op, void *G_host, const void *F_host, int opmode);
+int sgc_op_apply_host_chunked(const sgc_op *op, void *G_host, const void *F_host, int opmode, int nchunks);
+/* G OP C2(C1 F) on host arrays: the E -> H -> E' pass of two apply_curl! (curl.jl:52-137 twice), the intermediate
+ * field stays on the device.  Forward-z C1 with backward-z C2 is z-chunked and full-duplex (Bloch z: plane 0 of
+ * the result is finished last); other pairings run serially. */
+int sgc_op_apply_curlcurl_host(const sgc_op *c2, const sgc_op *c1, void *G_host, const void *F_host, int opmode,
+                               int nchunks);
+/* Page-locking of caller memory.  mode 1 (default): an array is registered the first time a *_host entry point
+ * sees it and stays registered (later calls copy at the pinned rate); the caller must call sgc_host_unregister
+ * before freeing such an array (the Julia shim does so in a finalizer).  mode 0: never register — pageable copies.
+ * sgc_host_register pins explicitly; sgc_host_unregister(NULL) drops every registration. */
+int sgc_host_set_registration(int mode);
+int sgc_host_register(const void *ptr, size_t bytes);
+int sgc_host_unregister(const void *ptr);
 
 /* ---------------------------------------------------------------------------------------- */
 /* Sparse assembly: create_* → SparseMatrixCSC{T,Int64}                                      */

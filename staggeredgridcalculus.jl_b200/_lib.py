@@ -109,6 +109,11 @@ _PROTOS = {
                                               C.c_int64, C.c_int64, C.c_void_p]),
     "sgc_op_set_slab_coef": (C.c_int, [C.c_void_p, dblp, dblp, C.c_int]),
     "sgc_op_apply_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
+    "sgc_op_apply_host_chunked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "sgc_op_apply_curlcurl_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "sgc_host_set_registration": (C.c_int, [C.c_int]),
+    "sgc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "sgc_host_unregister": (C.c_int, [C.c_void_p]),
     "sgc_asm_create_partial": (C.c_int, [vpp, C.c_int, i64p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, dblp,
                                          C.c_int]),
     "sgc_asm_create_mhat": (C.c_int, [vpp, C.c_int, i64p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

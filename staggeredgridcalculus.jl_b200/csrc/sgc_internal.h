@@ -132,10 +132,10 @@ struct sgc_op {
     sgc::cplx cz_ghost[2] = {{1.0, 0.0}, {1.0, 0.0}};  // α·∆z⁻¹ of the planes −1 / Nz (slab neighbours)
     int tile_x = 0, tile_y = 0, march = 0, variant = 0;
     void *arena = nullptr;        // device
-    // host-array convenience buffers
-    mutable void *dF = nullptr, *dG = nullptr;
-    mutable cudaStream_t hstream = nullptr;
+    // host-array entry points (sgc_host.cu): device staging buffers, three streams, events — created on first use
+    mutable struct sgc_hostpipe *hp = nullptr;
 };
+void sgc_hostpipe_destroy(struct sgc_hostpipe *hp);
 
 struct OpBuilder {
     std::vector<unsigned char> host;

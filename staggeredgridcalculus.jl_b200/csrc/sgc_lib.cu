@@ -226,9 +226,7 @@ static HV alpha_of(const double *alpha) {
 extern "C" int sgc_op_destroy(sgc_op *op) {
     if (!op) return SGC_OK;
     if (op->arena) cudaFree(op->arena);
-    if (op->dF) cudaFree(op->dF);
-    if (op->dG) cudaFree(op->dG);
-    if (op->hstream) cudaStreamDestroy(op->hstream);
+    if (op->hp) sgc_hostpipe_destroy(op->hp);
     delete op;
     return SGC_OK;
 }
@@ -748,22 +746,6 @@ extern "C" int sgc_op_launches(const sgc_op *op, int opmode) {
         add_mode = true;
     }
     return n;
-}
-
-extern "C" int sgc_op_apply_host(const sgc_op *op, void *G_host, const void *F_host, int opmode) {
-    REQUIRE(op && G_host && F_host, "NULL argument");
-    const size_t es = op->dtype == SGC_C128 ? 16 : 8;
-    const size_t bF = es * (size_t)op->M * op->n_in, bG = es * (size_t)op->M * op->n_out;
-    if (!op->hstream) CUDA_TRY(cudaStreamCreateWithFlags(&op->hstream, cudaStreamNonBlocking));
-    if (!op->dF) CUDA_TRY(cudaMalloc(&op->dF, bF));
-    if (!op->dG) CUDA_TRY(cudaMalloc(&op->dG, bG));
-    CUDA_TRY(cudaMemcpyAsync(op->dF, F_host, bF, cudaMemcpyHostToDevice, op->hstream));
-    if (opmode == SGC_OP_ADD) CUDA_TRY(cudaMemcpyAsync(op->dG, G_host, bG, cudaMemcpyHostToDevice, op->hstream));
-    int s = sgc_op_apply(op, op->dG, op->dF, opmode, op->hstream);
-    if (s) return s;
-    CUDA_TRY(cudaMemcpyAsync(G_host, op->dG, bG, cudaMemcpyDeviceToHost, op->hstream));
-    CUDA_TRY(cudaStreamSynchronize(op->hstream));
-    return SGC_OK;
 }
 
 // ---- one-shot calls -------------------------------------------------------------------------------

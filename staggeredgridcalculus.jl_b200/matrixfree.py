@@ -200,10 +200,27 @@ class Operator:
         a, b = pack(dzinv_below), pack(dzinv_above)
         check(lib.sgc_op_set_slab_coef(self._h, a, b, cc))
 
-    def apply_host(self, G: np.ndarray, F: np.ndarray, op="="):
-        """Host arrays in, host arrays out (column-major numpy arrays, modified in place)."""
-        assert G.flags.f_contiguous and F.flags.f_contiguous
-        check(lib.sgc_op_apply_host(self._h, C.c_void_p(G.ctypes.data), C.c_void_p(F.ctypes.data), opcode(op)))
+    def apply_host(self, G: np.ndarray, F: np.ndarray, op="=", nchunks=0):
+        """Host arrays in, host arrays out (column-major numpy arrays, G modified in place): `sgc_op_apply_host` —
+        the arrays are page-locked in place on first use, the pass is z-chunked and full-duplex."""
+        self._check_host(G, self.n_out)
+        self._check_host(F, self.n_in)
+        check(lib.sgc_op_apply_host_chunked(self._h, C.c_void_p(G.ctypes.data), C.c_void_p(F.ctypes.data), opcode(op), int(nchunks)))
+
+    def apply_after_host(self, first: "Operator", G: np.ndarray, F: np.ndarray, op="=", nchunks=0):
+        """`G OP self(first(F))` on host arrays in ONE library call (`sgc_op_apply_curlcurl_host`)."""
+        self._check_host(G, 3)
+        first._check_host(F, 3)
+        check(lib.sgc_op_apply_curlcurl_host(self._h, first._h, C.c_void_p(G.ctypes.data), C.c_void_p(F.ctypes.data),
+                                             opcode(op), int(nchunks)))
+
+    def _check_host(self, A: np.ndarray, ncomp):
+        want = np.complex128 if self.dtype_code == _lib.SGC_C128 else np.float64
+        M = int(np.prod(self.N, dtype=np.int64))
+        if A.dtype != want or A.size != M * ncomp or not (A.flags.f_contiguous or A.ndim == 1):
+            raise _lib.SgcError(_lib.SGC_ERR_INVALID, f"host array {A.shape} {A.dtype} does not match grid {self.N} x {ncomp} "
+                                f"components of {np.dtype(want).name} in column-major order")
+        _pin_for_lifetime(A)
 
     def set_slab(self, lo_interface: bool, hi_interface: bool):
         check(lib.sgc_op_set_slab(self._h, int(lo_interface), int(hi_interface)))
@@ -233,6 +250,35 @@ class Operator:
             self.destroy()
         except Exception:
             pass
+
+
+_PINNED = {}  # data pointer of the owning array -> weakref.finalize (drops the registration before the memory is freed)
+
+
+def _pin_for_lifetime(A: np.ndarray):
+    """The library page-locks host arrays in place and caches the registration (`sgc_host_register`); the
+    registration must be dropped before the memory is freed.  Tie it to the lifetime of the array that OWNS the
+    memory: its finaliser calls `sgc_host_unregister`."""
+    import weakref
+    owner = A
+    while isinstance(getattr(owner, "base", None), np.ndarray):
+        owner = owner.base
+    if getattr(owner, "base", None) is not None or not isinstance(owner, np.ndarray):
+        return  # memory owned by something else (mmap, torch, ...): leave it to the caller / pageable path
+    ptr = owner.ctypes.data
+    f = _PINNED.get(ptr)
+    if f is not None and f.alive:
+        return
+    lib.sgc_host_register(C.c_void_p(ptr), owner.nbytes)
+    _PINNED[ptr] = weakref.finalize(owner, _unpin, ptr)
+
+
+def _unpin(ptr):
+    _PINNED.pop(ptr, None)
+    try:
+        lib.sgc_host_unregister(C.c_void_p(ptr))
+    except Exception:
+        pass
 
 
 def _sync_and_destroy(op: Operator, stream):
