@@ -523,23 +523,47 @@ def main():
         leg.resync()
         e2e_step, e2e_mode, e2e_first_ms = e2e_step_serial, "serial: H2D, 2 curls, D2H", None
         if world == 1:
-            # ONE library call with ordinary (pageable) host arrays, as a Julia caller holding `Array`s would make it:
-            # sgc_op_apply_curlcurl_host page-locks the arrays in place on first sight (cached) and runs the z-chunked
-            # full-duplex pipeline (H2D | 2 fused curls per chunk | D2H on three streams) inside the library
+            # ONE library call per step (sgc_op_apply_curlcurl_host: the z-chunked full-duplex pipeline — H2D | 2 fused
+            # curls per chunk | D2H on three streams — lives inside the library).  Timed with host arrays in pinned
+            # memory from the library's allocator (sgc_malloc_host), and, as a second figure, with ordinary pageable
+            # numpy arrays, which the library page-locks in place on first sight (cached).
+            import ctypes as C2
             e2e_step_serial()
-            ref_out = Out_host.clone()
+            ref_np = Out_host.numpy().copy()
             E_np = E_host.numpy().copy()          # plain numpy arrays: NOT pinned by the caller
-            Out_np = np.zeros_like(E_np)
             E_host = Out_host = None
             op1, op2 = c_dual.backend.op, c_prim.backend.op
+            Out_np = np.zeros_like(E_np)
             t0 = time.perf_counter()
             op2.apply_after_host(op1, Out_np, E_np, "=", nchunks=args.e2e_chunks)
             e2e_first_ms = (time.perf_counter() - t0) * 1e3
-            if not np.array_equal(Out_np, ref_out.numpy()):
+            if not np.array_equal(Out_np, ref_np):
                 raise RuntimeError("sgc_op_apply_curlcurl_host disagrees with the serial host path")
-            e2e_step = lambda: op2.apply_after_host(op1, Out_np, E_np, "=", nchunks=args.e2e_chunks)
-            e2e_mode = (f"one C-ABI call per step (sgc_op_apply_curlcurl_host) on pageable numpy arrays: page-locked in place on the "
-                        f"first call ({e2e_first_ms:.0f} ms, not timed), then z-chunked ({args.e2e_chunks}) full-duplex pipeline inside the library")
+            for _ in range(2):
+                op2.apply_after_host(op1, Out_np, E_np, "=", nchunks=args.e2e_chunks)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                op2.apply_after_host(op1, Out_np, E_np, "=", nchunks=args.e2e_chunks)
+            e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / 5
+            lib.sgc_host_unregister(None)
+            Out_np = None
+
+            def pinned(n):  # numpy view of library-pinned host memory
+                p = C2.c_void_p()
+                check(lib.sgc_malloc_host(C2.byref(p), n * 16))
+                return np.ctypeslib.as_array(C2.cast(p, C2.POINTER(C2.c_double)), shape=(2 * n,)).view(np.complex128), p
+            E_pin, pE = pinned(3 * M)
+            Out_pin, pO = pinned(3 * M)
+            E_pin[:] = E_np
+            Out_pin[:] = 0
+            E_np = None
+            op2.apply_after_host(op1, Out_pin, E_pin, "=", nchunks=args.e2e_chunks)
+            if not np.array_equal(Out_pin, ref_np):
+                raise RuntimeError("sgc_op_apply_curlcurl_host (pinned arrays) disagrees with the serial host path")
+            e2e_step = lambda: op2.apply_after_host(op1, Out_pin, E_pin, "=", nchunks=args.e2e_chunks)
+            e2e_mode = (f"one C-ABI call per step (sgc_op_apply_curlcurl_host), host arrays in sgc_malloc_host memory; z-chunked "
+                        f"({args.e2e_chunks}) full-duplex pipeline inside the library; with ordinary pageable numpy arrays "
+                        f"(page-locked in place by the library, first call {e2e_first_ms:.0f} ms) {e2e_pageable_ms:.2f} ms per step")
         elif arena is not None and not args.serial_e2e:  # the same pipeline per rank; interface planes after a peer barrier
             from sgc_b200.hostpipe import HostSlabCurlCurl
             pipe = HostSlabCurlCurl(c_dual, c_prim, E, H, E2, nchunks=args.e2e_chunks)
@@ -567,10 +591,10 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         e2e_val = 2 * M * world * e2e_steps / e2e_s / 1e9
-        E_host = Out_host = E_np = Out_np = None
+        E_host = Out_host = None
         if world == 1:
-            from sgc_b200._lib import lib as _l
-            _l.sgc_host_unregister(None)
+            E_pin = Out_pin = e2e_step = None
+            lib.sgc_free_host(pE); lib.sgc_free_host(pO)
 
     peaks = {}
     try:
@@ -738,9 +762,18 @@ def bench_assembly(S, torch, peak, cplx=False):
 
 
 def bench_assembly_partitioned(S, torch, dist, rank, world):
-    """512³ Float64 all-Bloch create_curl, row-partitioned: rank r assembles the CSC block of its contiguous
-    row range (own colptr of length n+1; the blocks stack to the global matrix).  No exchange; the time is the
-    max over ranks, the rate the whole matrix's nnz over that time."""
+    """512³ Float64 all-Bloch create_curl partitioned over the ranks, both ways: (rows) rank r assembles the CSC
+    block of its contiguous row range (own colptr of length n+1; the blocks stack to the global matrix); (cols)
+    rank r assembles its block of columns — the global rowval / nzval are the concatenation of the blocks' arrays
+    and every rank does exactly 1/N of the single-GPU work.  No exchange; the time is the max over ranks, the rate
+    the whole matrix's nnz over that time."""
+    res = _bench_assembly_part(S, torch, dist, rank, world, by_cols=False)
+    cols = _bench_assembly_part(S, torch, dist, rank, world, by_cols=True)
+    res["column_partition"] = cols
+    return res
+
+
+def _bench_assembly_part(S, torch, dist, rank, world, by_cols):
     import ctypes as C
     from sgc_b200._lib import lib, check
     from sgc_b200.device import ints, int64s, scalars2, stream_handle
@@ -754,14 +787,24 @@ def bench_assembly_partitioned(S, torch, dist, rank, world):
         r0, r1 = row_range_for_rank(3 * M, rank, world)
         st = stream_handle()
         nnz = C.c_int64()
-        check(lib.sgc_asm_set_row_range(h, r0, r1))
+        ncols = 3 * M
+        if by_cols:
+            c0, c1 = C.c_int64(), C.c_int64()
+            check(lib.sgc_asm_col_partition(h, rank, world, C.byref(c0), C.byref(c1)))
+            check(lib.sgc_asm_set_col_range(h, c0.value, c1.value))
+            ncols = c1.value - c0.value
+        else:
+            check(lib.sgc_asm_set_row_range(h, r0, r1))
         check(lib.sgc_asm_count(h, C.byref(nnz), st))
-        colptr = torch.empty(3 * M + 1, dtype=torch.int64, device="cuda")
+        colptr = torch.empty(ncols + 1, dtype=torch.int64, device="cuda")
         rowval = torch.empty(nnz.value, dtype=torch.int64, device="cuda")
         nzval = torch.empty(nnz.value, dtype=torch.float64, device="cuda")
 
         def once():
-            check(lib.sgc_asm_set_row_range(h, r0, r1))  # drops the cached count: time the whole assembly
+            if by_cols:
+                check(lib.sgc_asm_set_col_range(h, c0.value, c1.value))  # drops the cached count: time the whole assembly
+            else:
+                check(lib.sgc_asm_set_row_range(h, r0, r1))
             check(lib.sgc_asm_count(h, C.byref(nnz), st))
             check(lib.sgc_asm_fill_all(h, C.c_void_p(colptr.data_ptr()), 1, C.c_void_p(rowval.data_ptr()),
                                        C.c_void_p(nzval.data_ptr()), st))
@@ -782,6 +825,10 @@ def bench_assembly_partitioned(S, torch, dist, rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         lib.sgc_asm_destroy(h)
         ms, total = float(tmax[0]), int(t[1])
+        if by_cols:
+            return {"workload": f"the same matrix as {world} per-GPU blocks of COLUMNS (global rowval / nzval = concatenation)",
+                    "nnz": total, "ms": ms, "nnz_per_s": total / (ms * 1e-3), "nnz_ok": total == 12 * M,
+                    "includes": "per rank: closed-form nnz and offsets + single fill pass over its columns (max over ranks)"}
         return {"workload": f"create_curl 512^3 Float64 all-Bloch, row-partitioned into {world} per-GPU CSC blocks (no exchange)",
                 "nnz": total, "ms": ms, "nnz_per_s": total / (ms * 1e-3), "nnz_ok": total == 12 * M,
                 "includes": "per rank: count pass + device scan + nnz read-back + single fill pass (max over ranks)"}

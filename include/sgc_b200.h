@@ -327,6 +327,17 @@ int sgc_asm_create_picmp(sgc_asm **a, int ndim, const int64_t *N, int Kf, const 
  * concatenation of the blocks of a partition of 0..m equals the global matrix. */
 int sgc_asm_set_row_range(sgc_asm *a, int64_t row_begin, int64_t row_end);
 
+/* Column partition (the scalable multi-GPU form): assemble only the columns [col_begin, col_end) (0-based,
+ * half-open) as a stand-alone m x (col_end - col_begin) CSC block with GLOBAL row indices — the horizontal
+ * concatenation of the blocks of a partition of 0..n is the global matrix, i.e. the global rowval / nzval are the
+ * plain concatenation of the blocks' arrays (matrix/differential/curl.jl:103) and the global colptr is each
+ * block's colptr shifted by the entries before it.  Every rank does exactly its share of the single-GPU work:
+ * the closed-form offsets hold for any column range, so there is no count pass, scan or read-back.  Range ends
+ * must be multiples of 128 * (order_cmpfirst ? Kin : 1) columns (or n); sgc_asm_col_partition returns the range of
+ * part `part` of `nparts` balanced, aligned parts.  Cannot be combined with a row range. */
+int sgc_asm_col_partition(const sgc_asm *a, int part, int nparts, int64_t *col_begin, int64_t *col_end);
+int sgc_asm_set_col_range(sgc_asm *a, int64_t col_begin, int64_t col_end);
+
 /* m, n of the (block of the) matrix and its value type (SGC_F64 / SGC_C128 =
  * promote_type of the inputs, curl.jl:59). */
 int sgc_asm_shape(const sgc_asm *a, int64_t *m, int64_t *n, int *val_dtype);

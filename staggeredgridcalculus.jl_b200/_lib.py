@@ -126,6 +126,8 @@ _PROTOS = {
     "sgc_asm_create_picmp": (C.c_int, [vpp, C.c_int, i64p, C.c_int, intp, C.c_void_p, C.c_int, C.c_int]),
     "sgc_asm_set_row_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "sgc_asm_set_tuning": (C.c_int, [C.c_void_p, C.c_int]),
+    "sgc_asm_col_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int, i64p, i64p]),
+    "sgc_asm_set_col_range": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "sgc_asm_shape": (C.c_int, [C.c_void_p, i64p, i64p, intp]),
     "sgc_asm_count": (C.c_int, [C.c_void_p, i64p, C.c_void_p]),
     "sgc_asm_fill_all": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

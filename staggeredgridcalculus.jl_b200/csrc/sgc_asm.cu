@@ -165,6 +165,7 @@ static int finish_asm(sgc_asm *a) {
         }
         a->set_total[set] = a->N[1] * a->N[2] * S[0] + a->N[0] * a->N[2] * S[1] + a->N[0] * a->N[1] * S[2];
     }
+    a->h_prefix = pre;
     CUDA_TRY(cudaMalloc((void **)&a->prefix_tables, sizeof(int64_t) * pre.size()));
     CUDA_TRY(cudaMemcpy(a->prefix_tables, pre.data(), sizeof(int64_t) * pre.size(), cudaMemcpyHostToDevice));
     return SGC_OK;
@@ -293,8 +294,55 @@ extern "C" int sgc_asm_create_picmp(sgc_asm **a_out, int ndim, const int64_t *N,
 extern "C" int sgc_asm_set_row_range(sgc_asm *a, int64_t row_begin, int64_t row_end) {
     REQUIRE(a, "handle is NULL");
     REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= (int64_t)a->Kout * a->M, "row range out of bounds");
+    REQUIRE(a->col_end < 0 || (row_begin == 0 && row_end == (int64_t)a->Kout * a->M), "a row range cannot be combined with a column range");
     a->row_begin = row_begin;
     a->row_end = row_end;
+    a->nnz = -1;
+    a->counted = false;
+    return SGC_OK;
+}
+
+// entries stored before group g of the whole matrix (host evaluation of prefix_entries_before)
+static int64_t host_entries_before(const sgc_asm *a, int64_t g) {
+    const int64_t ngroups = a->cmpfirst ? a->M : (int64_t)a->Kin * a->M;
+    if (g >= ngroups) return a->set_total[3];
+    int set = 3;
+    int64_t c = g, base = 0;
+    if (!(a->cmpfirst && a->Kin > 1) && a->Kin != 1) {
+        set = (int)(g / a->M);
+        c = g - (int64_t)set * a->M;
+        for (int q = 0; q < set; ++q) base += a->set_total[q];
+    }
+    const int64_t Nx = a->N[0], Ny = a->N[1];
+    const int64_t t = c / Nx, i = c - t * Nx, k = t / Ny, j = t - k * Ny;
+    const int64_t *PA = a->h_prefix.data() + a->prefix_off[set][0], *PB = a->h_prefix.data() + a->prefix_off[set][1],
+                  *PC = a->h_prefix.data() + a->prefix_off[set][2];
+    const int64_t SA = PA[Nx], SB = PB[Ny];
+    const int64_t bj = PB[j + 1] - PB[j], ck = PC[k + 1] - PC[k];
+    return base + k * (Ny * SA + Nx * SB) + Nx * Ny * PC[k] + j * SA + Nx * PB[j] + j * Nx * ck + PA[i] + i * (bj + ck);
+}
+
+static int64_t asm_col_align(const sgc_asm *a) { return (int64_t)128 * (a->cmpfirst ? a->Kin : 1); }  // columns per CTA
+
+extern "C" int sgc_asm_col_partition(const sgc_asm *a, int part, int nparts, int64_t *col_begin, int64_t *col_end) {
+    REQUIRE(a && col_begin && col_end, "NULL argument");
+    REQUIRE(nparts >= 1 && part >= 0 && part < nparts, "part %d outside 0..%d", part, nparts - 1);
+    const int64_t ncol = (int64_t)a->Kin * a->M, al = asm_col_align(a);
+    const int64_t ncta = (ncol + al - 1) / al;
+    *col_begin = std::min(ncol, (ncta * part / nparts) * al);
+    *col_end = std::min(ncol, (ncta * (part + 1) / nparts) * al);
+    return SGC_OK;
+}
+
+extern "C" int sgc_asm_set_col_range(sgc_asm *a, int64_t col_begin, int64_t col_end) {
+    REQUIRE(a, "handle is NULL");
+    const int64_t ncol = (int64_t)a->Kin * a->M, al = asm_col_align(a);
+    REQUIRE(0 <= col_begin && col_begin <= col_end && col_end <= ncol, "column range out of bounds");
+    REQUIRE(a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M, "a column range cannot be combined with a row range");
+    REQUIRE(col_begin % al == 0 || col_begin == ncol, "col_begin must be a multiple of %lld columns (use sgc_asm_col_partition)", (long long)al);
+    REQUIRE(col_end % al == 0 || col_end == ncol, "col_end must be a multiple of %lld columns or the last column", (long long)al);
+    a->col_begin = col_begin;
+    a->col_end = (col_begin == 0 && col_end == ncol) ? -1 : col_end;
     a->nnz = -1;
     a->counted = false;
     return SGC_OK;
@@ -311,7 +359,7 @@ extern "C" int sgc_asm_set_tuning(sgc_asm *a, int force_count_pass) {
 extern "C" int sgc_asm_shape(const sgc_asm *a, int64_t *m, int64_t *n, int *val_dtype) {
     REQUIRE(a, "handle is NULL");
     if (m) *m = a->row_end - a->row_begin;
-    if (n) *n = (int64_t)a->Kin * a->M;
+    if (n) *n = a->col_end < 0 ? (int64_t)a->Kin * a->M : a->col_end - a->col_begin;
     if (val_dtype) *val_dtype = a->cx ? SGC_C128 : SGC_F64;
     return SGC_OK;
 }
@@ -352,6 +400,13 @@ static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
         p.wrap_span = span;
     }
     p.prefix_enabled = (a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M && a->prefix_tables && !a->force_count_pass) ? 1 : 0;
+    p.cta_first = 0; p.g_end = p.ngroups; p.col_base = 0; p.entry_base = 0;
+    if (a->col_end >= 0) {
+        p.cta_first = a->cta_first;
+        p.g_end = a->col_end / p.cols_per_group;
+        p.col_base = a->col_begin;
+        p.entry_base = a->entry_base;
+    }
     int64_t before = 0;
     for (int set = 0; set < 4; ++set) {
         for (int ax = 0; ax < 3; ++ax) p.prefix[set][ax] = a->prefix_tables + a->prefix_off[set][ax];
@@ -415,6 +470,18 @@ static int asm_count(sgc_asm *a, cudaStream_t st) {
     const int64_t ngroups = a->cmpfirst ? a->M : (int64_t)a->Kin * a->M;
     const int64_t ncta = (ngroups + ASM_BLOCK - 1) / ASM_BLOCK;
     REQUIRE(ncta < (int64_t)0x7fffffff, "matrix too large for one launch");
+    if (a->col_end >= 0) {
+        // a block of columns of the whole matrix: same closed form, evaluated at both ends of the range
+        REQUIRE(a->prefix_tables && !a->force_count_pass, "a column range needs the closed-form offsets");
+        const int cpg = a->cmpfirst ? a->Kin : 1;
+        const int64_t gb = a->col_begin / cpg, ge = a->col_end / cpg;
+        a->cta_first = gb / ASM_BLOCK;
+        a->ncta = (ge - gb + ASM_BLOCK - 1) / ASM_BLOCK;
+        a->entry_base = host_entries_before(a, gb);
+        a->nnz = host_entries_before(a, ge) - a->entry_base;
+        a->counted = true;
+        return SGC_OK;
+    }
     if (ncta != a->ncta || !a->cta_total) {
         if (a->cta_total) cudaFree(a->cta_total);
         if (a->cta_offset) cudaFree(a->cta_offset);

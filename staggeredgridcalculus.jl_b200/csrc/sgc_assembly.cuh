@@ -60,6 +60,8 @@ struct AsmParams {
     int prefix_enabled;
     const int64_t *prefix[4][3];  // [set][axis] → int64[N_axis + 1], exclusive prefix sums
     int64_t set_base[4];          // entries before the first group of the set
+    // column partition: groups [cta_first·BLOCK, g_end) are processed; outputs are re-based to the block
+    int64_t cta_first, g_end, col_base, entry_base;
 };
 
 // entries stored before group g (= before its first column) when all rows are kept
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
     __shared__ int s_warp[64];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr bool WRITES = (MODE == ASM_FILL || MODE == ASM_FILL_ALL);
-    const int64_t g0 = (int64_t)blockIdx.x * BLOCK;
+    const int64_t g0 = ((int64_t)blockIdx.x + p.cta_first) * BLOCK;
     const int64_t g = g0 + threadIdx.x;
     if (p.skip_enabled) {
         const int64_t g1 = min(g0 + (int64_t)BLOCK, p.ngroups);
@@ -297,7 +299,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             return;
         }
     }
-    const bool live = g < p.ngroups;
+    const bool live = g < p.g_end;
     int nu0 = 0;
     IDX c = 0, sub[3] = {0, 0, 0};
     if (live) group_decode<T, IDX>(p, g, nu0, c, sub);
@@ -334,10 +336,11 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
         return;
     }
     // absolute (0-based) position of this CTA's first entry
-    const int64_t col0 = g0 * NCOLS;
+    const int64_t col0 = g0 * NCOLS - p.col_base;  // (column index within the block of columns being assembled)
+    const int64_t ncol_out = p.g_end * NCOLS - p.col_base;
     int64_t base;
     if (MODE == ASM_FILL) base = colptr_in[col0] - p.index_base;
-    else if (p.prefix_enabled) base = prefix_entries_before<T, IDX>(p, g0);  // closed form: no count pass, no scan
+    else if (p.prefix_enabled) base = prefix_entries_before<T, IDX>(p, g0) - p.entry_base;  // closed form: no count pass, no scan
     else base = cta_offset[blockIdx.x];
     constexpr int PADK = NCOLS * E;  // entry slots per thread
     if (total == BLOCK * PADK) {
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
                 const int c = threadIdx.x + q * BLOCK;
                 colptr_out[col0 + c] = base + ib + (int64_t)E * c;
             }
-            if (g == p.ngroups - 1) colptr_out[p.ncol] = base + ib + total;
+            if (g == p.g_end - 1) colptr_out[ncol_out] = base + ib + total;
             if (MODE == ASM_COLPTR) return;
         }
         if (WRITES) {
@@ -400,10 +403,10 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             int64_t o = base + off0 + p.index_base;
 #pragma unroll
             for (int q = 0; q < NCOLS; ++q) { s_colptr[threadIdx.x * NCOLS + q] = o; o += cnt[q]; }
-            if (g == p.ngroups - 1) colptr_out[p.ncol] = o;  // one-past-the-end entry
+            if (g == p.g_end - 1) colptr_out[ncol_out] = o;  // one-past-the-end entry
         }
         __syncthreads();
-        const int64_t ncols_cta = min((int64_t)BLOCK * NCOLS, p.ncol - col0);
+        const int64_t ncols_cta = min((int64_t)BLOCK * NCOLS, ncol_out - col0);
         for (int q = threadIdx.x; q < ncols_cta; q += BLOCK) colptr_out[col0 + q] = s_colptr[q];
         if (MODE == ASM_COLPTR) return;
     }

@@ -3,12 +3,95 @@
 #include "sgc_internal.h"
 
 #include <algorithm>
+#include <cmath>
+#include <type_traits>
 
 #include "sgc_curlcurl.cuh"
+#include "sgc_cc4.cuh"
 
 using namespace sgc;
 
 namespace {
+
+// ---- fourth generation (sgc_cc4.cuh): TMA-fed, warp-specialised ----------------------------------------------------
+// cuTensorMapEncodeTiled comes from the driver; the library links the runtime only, so the entry point is looked up.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<void *> cached{nullptr};
+    void *f = cached.load(std::memory_order_acquire);
+    if (!f) {
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        cached.store(f, std::memory_order_release);
+    }
+    return (EncodeTiledFn)f;
+}
+
+// one ComplexF64 component array (Nx, Ny, Nz) as a 3-D tensor of Float64 pairs; box = one (TX+2) x (TY+2) tile plane
+int encode_component(CUtensorMap *tm, const cplx *base, int Nx, int Ny, int Nz, int box_x, int box_y) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return sgc_fail(SGC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[3] = {(cuuint64_t)2 * Nx, (cuuint64_t)Ny, (cuuint64_t)Nz};
+    const cuuint64_t strides[2] = {(cuuint64_t)Nx * 16, (cuuint64_t)Nx * Ny * 16};  // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)2 * box_x, (cuuint32_t)box_y, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sgc_fail(SGC_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return SGC_OK;
+}
+
+template <typename C, bool ADD, int TY, int SE, int SH, bool FZ1, bool FZ2>
+int launch_cc4_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = cc4_smem_bytes(TY, SE, SH);
+    auto kern = k_cc4<C, ADD, TY, SE, SH, FZ1, FZ2>;
+    static std::atomic<uint64_t> attr_devices{0};
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
+    kern<<<grid, dim3(32 * (2 * TY + 3), 1, 1), smem, st>>>(P);
+    return SGC_OK;
+}
+template <typename C, bool ADD, int TY, int SE, int SH>
+int launch_cc4_dirs(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
+    if (P.q.fwd1[2]) return P.q.fwd2[2] ? launch_cc4_one<C, ADD, TY, SE, SH, true, true>(P, grid, st)
+                                        : launch_cc4_one<C, ADD, TY, SE, SH, true, false>(P, grid, st);
+    return P.q.fwd2[2] ? launch_cc4_one<C, ADD, TY, SE, SH, false, true>(P, grid, st)
+                       : launch_cc4_one<C, ADD, TY, SE, SH, false, false>(P, grid, st);
+}
+template <typename C, bool ADD>
+int launch_cc4_tiles(const CurlCurl4Params<C> &P, int ty, int se, int sh, dim3 grid, cudaStream_t st) {
+#define CC4_CASE(TY, SE, SH) if (ty == TY && se == SE && sh == SH) return launch_cc4_dirs<C, ADD, TY, SE, SH>(P, grid, st);
+    CC4_CASE(8, 4, 3)
+    CC4_CASE(8, 5, 4)
+    CC4_CASE(6, 4, 3)
+    CC4_CASE(10, 4, 3)
+    CC4_CASE(12, 4, 3)
+#undef CC4_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (TMA): tile 32x%d with %d/%d stages is not built", ty, se, sh);
+}
+
+// z-march that fills whole waves of one-CTA-per-SM: among the chunk counts with a march of at least 16 planes, the
+// one whose last wave is fullest (ties: the longer march, i.e. fewer halo planes)
+int cc4_march(int64_t tiles, int64_t nk) {
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double best = -1.0;
+    int best_march = (int)std::min<int64_t>(nk, 64);
+    for (int64_t chunks = 1; chunks <= nk; ++chunks) {
+        const int64_t march = (nk + chunks - 1) / chunks;
+        if (march < 16 && chunks > 1) break;
+        const int64_t ctas = tiles * ((nk + march - 1) / march);
+        const double waves = (double)ctas / sms;
+        const double eff = waves / std::ceil(waves) * ((double)march / (march + 2));
+        if (eff > best + 1e-9) { best = eff; best_march = (int)march; }
+    }
+    return best_march;
+}
 
 template <typename T, typename C, bool ADD, int TX, int TY, int SE, int MINB>
 int launch_cc_one(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
@@ -111,6 +194,35 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
     dim3 grid((unsigned)((p.Nx + tx - 1) / tx), (unsigned)((p.Ny + ty - 1) / ty), (unsigned)((nk + p.march - 1) / p.march));
     if (grid.y > 65535 || grid.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
     if ((int64_t)p.Nx * p.Ny >= (int64_t)0x7fffffff) return sgc_fail(SGC_ERR_INVALID, "plane too large for the fused curl-of-curl");
+    // default for ComplexF64 fields on grids that hold a whole tile: the TMA-fed warp-specialised kernel (variant 2 / 1
+    // select the third / first generation)
+    if constexpr (std::is_same<T, cplx>::value) {
+        // version 0: automatic (tuning knobs that do not name a built configuration fall back to the defaults);
+        // version 4: as given (an unbuilt configuration is an error)
+        auto built = [](int ty, int se, int sh) {
+            return (ty == 8 && ((se == 4 && sh == 3) || (se == 5 && sh == 4))) || ((ty == 6 || ty == 10 || ty == 12) && se == 4 && sh == 3);
+        };
+        int ty4 = c2->tile_y ? c2->tile_y : 8;
+        int se4 = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 4;
+        int sh4 = ((c2->variant >> 8) & 0xF) ? ((c2->variant >> 8) & 0xF) : 3;
+        if (version == 0 && !built(ty4, se4, sh4)) { ty4 = 8; se4 = 4; sh4 = 3; }
+        if ((version == 0 || version == 4) && p.Nx >= 34 && p.Ny >= ty4 + 2 && ((uintptr_t)F % 16 == 0)) {
+            CurlCurl4Params<C> P{};
+            P.q = p;
+            int s4 = SGC_OK;
+            for (int d = 0; d < 3 && !s4; ++d) s4 = encode_component(&P.tm[d], p.F[d], p.Nx, p.Ny, p.Nz, 34, ty4 + 2);
+            if (!s4) {
+                const int64_t tiles = (int64_t)((p.Nx + 31) / 32) * ((p.Ny + ty4 - 1) / ty4);
+                P.q.march = (c2->march > 0 && version == 4) ? c2->march : cc4_march(tiles, nk);
+                dim3 g4((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty4 - 1) / ty4), (unsigned)((nk + P.q.march - 1) / P.q.march));
+                if (g4.y > 65535 || g4.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
+                s4 = add_mode ? launch_cc4_tiles<C, true>(P, ty4, se4, sh4, g4, st) : launch_cc4_tiles<C, false>(P, ty4, se4, sh4, g4, st);
+                if (s4) return s4;
+                return sgc_check_launch("k_cc4");
+            }
+            // no tensor-map support in this driver: fall through to the third generation
+        }
+    }
     int s;
     if (version == 1) s = add_mode ? launch_cc_tiles<T, C, true>(p, tx, ty, se, grid, st) : launch_cc_tiles<T, C, false>(p, tx, ty, se, grid, st);
     else s = add_mode ? launch_ccw_tiles<T, C, true>(p, ty, se, grid, st) : launch_ccw_tiles<T, C, false>(p, ty, se, grid, st);

@@ -87,7 +87,19 @@ class _Asm:
             self.h = None
 
 
+def col_partition(a: "_Asm", part, nparts):
+    """Aligned, balanced column range of part `part` of `nparts` (`sgc_asm_col_partition`)."""
+    c0, c1 = C.c_int64(), C.c_int64()
+    check(lib.sgc_asm_col_partition(a.h, int(part), int(nparts), C.byref(c0), C.byref(c1)))
+    return c0.value, c1.value
+
+
 def _finish(a: _Asm, index_base, row_range, method, device, stream=None) -> DeviceCSC:
+    if isinstance(row_range, dict):  # {"cols": (part, nparts)} or {"cols": (col_begin, col_end, "abs")}: a block of COLUMNS
+        spec = row_range["cols"]
+        c0, c1 = (spec[0], spec[1]) if len(spec) == 3 else col_partition(a, spec[0], spec[1])
+        check(lib.sgc_asm_set_col_range(a.h, int(c0), int(c1)))
+        row_range = None
     if row_range is not None:
         check(lib.sgc_asm_set_row_range(a.h, int(row_range[0]), int(row_range[1])))
     m, n, vt = C.c_int64(), C.c_int64(), C.c_int()

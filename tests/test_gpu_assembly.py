@@ -198,6 +198,47 @@ def test_row_partition_on_a_tall_grid_skips_far_columns(S):
                 assert np.array_equal(stacked.data, full.data), what
 
 
+def test_column_partition_blocks_concatenate_to_the_global_arrays(S):
+    """The scalable multi-GPU form (`sgc_asm_set_col_range`): the block of columns of part p is a stand-alone CSC
+    matrix with global row indices, and the GLOBAL rowval / nzval are the plain concatenation of the blocks' arrays
+    (colptr: each block's shifted by the entries before it) — bit for bit, both orderings, Bloch and symmetric
+    boundaries, real and complex values, curl / divergence / gradient / mean, 128³ included."""
+    rng = np.random.default_rng(18)
+    cases = []
+    for N in ((40, 12, 9), (128, 128, 128)):
+        dl = [rand_coef(rng, n, False) for n in N]
+        dlc = [rand_coef(rng, n, True) for n in N]
+        e = [np.exp(-0.1j), np.exp(-0.2j), np.exp(-0.3j)]
+        big = N[0] == 128
+        cases.append((N, "curl f64", lambda N=N, dl=dl, **kw: S.create_curl([True, False, True], dl, [True, True, True], [1.0] * 3, **kw)))
+        if big:
+            continue
+        cases.append((N, "curl c128 mixed BC", lambda N=N, dlc=dlc, e=e, **kw: S.create_curl([True, False, True], dlc, [False, True, False], e, **kw)))
+        cases.append((N, "curl block ordering", lambda N=N, dl=dl, e=e, **kw: S.create_curl([False, True, True], dl, [True, False, True], e, order_cmpfirst=False, **kw)))
+        cases.append((N, "divg", lambda N=N, dl=dl, e=e, **kw: S.create_divg([False, True, True], dl, [True, False, True], e, **kw)))
+        cases.append((N, "grad", lambda N=N, dl=dl, e=e, **kw: S.create_grad([True, True, False], dl, [False, True, True], e, **kw)))
+        cases.append((N, "mean", lambda N=N, dl=dl, **kw: S.create_mean([True, False, True], dl, dl, [True, False, True], **kw)))
+    for N, name, make in cases:
+        full = make()
+        cp, rv, nz = full.to_host()
+        for nparts in ((8,) if N[0] == 128 else (1, 2, 3, 8)):
+            cps, rvs, nzs, ncols, off = [], [], [], 0, 0
+            for part in range(nparts):
+                blk = make(row_range={"cols": (part, nparts)})
+                assert blk.m == full.m
+                bcp, brv, bnz = blk.to_host()
+                assert bcp[0] == 1 and bcp[-1] == 1 + len(brv)
+                cps.append(bcp[:-1] + off)
+                rvs.append(brv); nzs.append(bnz)
+                off += len(brv)
+                ncols += blk.n
+            what = f"{name} {N} in {nparts} column blocks"
+            assert ncols == full.n, what
+            assert np.array_equal(np.concatenate(cps + [np.array([1 + off])]), cp), what + ": colptr"
+            assert np.array_equal(np.concatenate(rvs), rv), what + ": rowval"
+            assert np.array_equal(np.concatenate(nzs), nz), what + ": nzval"
+
+
 @pytest.mark.parametrize("isfwd", [[True, True, True], [True, False, True]])
 def test_curl_of_curl_invariants_with_device_matrices(S, isfwd):
     """test/curl.jl:123-186 with the matrices assembled on the GPU: `Cv*Cu` has diagonal 4, 13 nonzeros per row, is

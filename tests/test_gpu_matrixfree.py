@@ -431,9 +431,12 @@ def test_fused_divg_grad_slab_split_equals_whole(S):
 # ------------------------------------------------------------------------------------------------
 # fused curl-of-curl (k_curlcurl3): one pass, H never written — bit-identical to two apply_curl!
 # ------------------------------------------------------------------------------------------------
-# (tile_x, tile_y, march, E-ring stages, kernel version: 0 = warp roles, 1 = first generation)
-CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 8, 3, 3, 0), (32, 7, 5, 4, 0), (32, 4, 2, 4, 0), (32, 7, 1, 3, 0), (32, 4, 7, 3, 0),
-                    (32, 8, 3, 3, 1), (32, 4, 2, 4, 1), (64, 4, 6, 3, 1)]
+# (tile_x, tile_y, march, ring stages, kernel version): version 0 = automatic (the TMA-fed warp-specialised kernel
+# k_cc4 for ComplexF64 grids that hold a tile, else the third generation), 4 = k_cc4 as configured (stages = E ring |
+# H ring << 4), 2 = third generation (warp roles, cp.async), 1 = first generation
+CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 8, 3, 3, 2), (32, 7, 5, 4, 2), (32, 4, 2, 4, 2), (32, 7, 1, 3, 2), (32, 4, 7, 3, 2),
+                    (32, 8, 3, 3, 1), (32, 4, 2, 4, 1), (64, 4, 6, 3, 1),
+                    (32, 8, 3, 0x34, 4), (32, 8, 1, 0x45, 4), (32, 6, 5, 0x34, 4), (32, 10, 2, 0x34, 4), (32, 12, 7, 0x34, 4)]
 
 
 def _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, tilings, what):
@@ -482,7 +485,7 @@ def test_fused_curlcurl_equals_two_curls(S, N, cplx_field, cplx_coef):
         for isbloch in ([True] * 3, [False] * 3, [True, False, True], [False, True, False]):
             if not all(isbloch[d] or N[d] >= 2 or not (isfwd1[d] or isfwd2[d]) for d in range(3)):
                 continue  # forward + symmetric on an axis of length 1 is rejected (reads Fu[2])
-            _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, CURLCURL_TILINGS[:3] + CURLCURL_TILINGS[6:7],
+            _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, CURLCURL_TILINGS[:3] + CURLCURL_TILINGS[6:7] + CURLCURL_TILINGS[9:10],
                            f"curlcurl N={N} fwd1={isfwd1} fwd2={isfwd2} bloch={isbloch}")
 
 

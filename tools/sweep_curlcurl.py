@@ -30,14 +30,20 @@ for bl in ([False] * 3, [True] * 3):
         c1.apply(H, E, "="); c2.apply(Gref, H, "=")
     ms2 = timeit(two)
     print(json.dumps(dict(bloch=bl[0], mode="two fused curls", ms=round(ms2, 4), gcell_pairs=round(M / ms2 / 1e6, 2), gbs_192=round(192 * M / ms2 / 1e6))), flush=True)
-    for tx, ty, se, ver in ((32, 8, 3, 0), (32, 7, 3, 0), (32, 7, 4, 0), (32, 4, 3, 0), (32, 4, 4, 0), (32, 8, 3, 1)):
-        for march in (16, 32, 64):
+    # ver 4: TMA-fed warp-specialised kernel (se = E stages | H stages << 4), ver 2: third generation (warp roles, cp.async)
+    cfgs = [(32, 8, 0x34, 4, m) for m in (0, 32, 64, 128)] + [(32, 8, 0x45, 4, m) for m in (0, 64)] + \
+           [(32, 6, 0x34, 4, m) for m in (0, 64)] + [(32, 10, 0x34, 4, m) for m in (0, 64)] + [(32, 12, 0x34, 4, m) for m in (0, 64)] + \
+           [(32, 7, 3, 2, 64), (32, 8, 3, 2, 64)]
+    if len(sys.argv) > 2 and sys.argv[2] == "quick":
+        cfgs = [(32, 8, 0x34, 4, 0), (32, 6, 0x34, 4, 0), (32, 7, 3, 2, 64)]
+    for tx, ty, se, ver, march in cfgs:
+        for _ in (0,):
             c2.set_tuning(tx, ty, march, (se << 4) | ver)
             try:
                 ms = timeit(lambda: c2.apply_after(c1, G, E, "="))
                 ok = bool(torch.equal(torch.view_as_real(G.t), torch.view_as_real(Gref.t)))
                 print(json.dumps(dict(bloch=bl[0], ver=ver, tx=tx, ty=ty, se=se, march=march, ms=round(ms, 4), speedup=round(ms2 / ms, 3),
-                                      gbs_96=round(96 * M / ms / 1e6), ok=ok)), flush=True)
+                                      gbs_96=round(96 * M / ms / 1e6), ok=ok, ndiff=int((torch.view_as_real(G.t) != torch.view_as_real(Gref.t)).sum()))), flush=True)
             except Exception as ex:
                 print(json.dumps(dict(tx=tx, ty=ty, se=se, march=march, err=str(ex)[:100])), flush=True)
     c2.set_tuning(0, 0, 0, 0)
