@@ -285,6 +285,27 @@ int sgc_host_register(const void *ptr, size_t bytes);
 int sgc_host_unregister(const void *ptr);
 
 /* ---------------------------------------------------------------------------------------- */
+/* Device-side producers of the per-axis vectors: PML-stretched spacings      */
+/* s∆l = s(l)·∆l of create_stretched_∆l / create_sfactor / calc_sfactor (src/pml.jl:94-153) and   */
+/* their inverses (invert_∆l, src/util.jl:42-48), so that a frequency sweep never round-trips     */
+/* through the host.  One sgc_axis = one axis of a Grid (grid.jl:125-207), primal or dual set.    */
+/* ---------------------------------------------------------------------------------------- */
+typedef struct sgc_axis sgc_axis;
+/* l[i]: locations of the n points (HOST), dl[i]: their spacings (HOST); lpml_neg / lpml_pos: PML interface
+ * locations, Lpml_neg / Lpml_pos: PML thicknesses (pml_loc, pml.jl:165-174); pml: {m, R, κmax, amax, ma} or NULL for
+ * PMLParam() = {4, exp(-16), 1, 0, 4}.  The ω-independent profiles σ(d), κ(d), a(d) are tabulated once (host
+ * log / pow) and kept on the device. */
+int sgc_axis_create(sgc_axis **ax, int64_t n, const double *l, const double *dl, double lpml_neg, double lpml_pos,
+                    double Lpml_neg, double Lpml_pos, const double *pml);
+int sgc_axis_destroy(sgc_axis *ax);
+/* s∆l and / or (s∆l)⁻¹ at angular frequency ω into DEVICE arrays of n ComplexF64 (either may be NULL). */
+int sgc_axis_stretch(const sgc_axis *ax, double omega, void *sdl_device, void *sdl_inv_device, void *stream);
+/* Rebuild the coefficient tables of an operator handle for a new ω on the device: for every ∂ term along array
+ * dimension d, c[i] = (parity·α)·(s∆l_d[i])⁻¹ from axes[d].  For ∂ / curl / divergence / gradient operators created
+ * with ComplexF64 coefficient vectors of the same lengths; queued on `stream`, no host round-trip. */
+int sgc_op_set_axes(sgc_op *op, const sgc_axis *const *axes, double omega, void *stream);
+
+/* ---------------------------------------------------------------------------------------- */
 /* Sparse assembly: create_* → SparseMatrixCSC{T,Int64}                                      */
 /* Two steps, so that the caller owns the output arrays (Julia Vectors or device buffers):   */
 /*   sgc_asm_create_*  describe the operator (host work O(ΣN));                               */

@@ -114,6 +114,10 @@ _PROTOS = {
     "sgc_host_set_registration": (C.c_int, [C.c_int]),
     "sgc_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "sgc_host_unregister": (C.c_int, [C.c_void_p]),
+    "sgc_axis_create": (C.c_int, [vpp, C.c_int64, dblp, dblp, C.c_double, C.c_double, C.c_double, C.c_double, dblp]),
+    "sgc_axis_destroy": (C.c_int, [C.c_void_p]),
+    "sgc_axis_stretch": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgc_op_set_axes": (C.c_int, [C.c_void_p, vpp, C.c_double, C.c_void_p]),
     "sgc_asm_create_partial": (C.c_int, [vpp, C.c_int, i64p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, dblp,
                                          C.c_int]),
     "sgc_asm_create_mhat": (C.c_int, [vpp, C.c_int, i64p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -215,24 +215,7 @@ __global__ void __launch_bounds__(32 * (2 * TY + 3), 1) k_cc4(const __grid_const
             }
         };
         for (int j = 0; j < nslots + (patch ? LAG : 0); ++j) {
-            if (j < nslots) {
-                int kp, ghost;
-                plane_of(j, kp, ghost);
-                mbar_wait(bar_eempty + 8 * issue.stage, issue.phase ^ 1u);  // the H-warps are done with this stage
-                const unsigned st = sE + issue.stage * ESTAGE;
-                if (ghost) {  // (patch mode) the whole tile by software copies
-                    soft_fill(st, kp, ghost, true);
-                    cp_async_mbar_arrive_noinc(bar_efull + 8 * issue.stage);
-                } else if (lane == 0) {
-                    const unsigned bar = patch ? bar_tma + 8 * issue.stage : bar_efull + 8 * issue.stage;
-                    if (patch) fence_proxy_async();
-                    mbar_arrive_expect_tx(bar, 3 * ECOMP * ES);
-                    tma_load_3d(st, &P.tm[0], bar, 2 * ex0, ey0, kp);
-                    tma_load_3d(st + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp);
-                    tma_load_3d(st + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp);
-                }
-                issue.advance<SE>();
-            }
+            // (patch first: the H-warps free the stage slot j wants only after slot j − SE + 1 — patched here — is full)
             if (patch && j >= LAG) {
                 int kp, ghost;
                 plane_of(j - LAG, kp, ghost);
@@ -242,6 +225,25 @@ __global__ void __launch_bounds__(32 * (2 * TY + 3), 1) k_cc4(const __grid_const
                     cp_async_mbar_arrive_noinc(bar_efull + 8 * fix.stage);
                 }
                 fix.advance<SE>();
+            }
+            if (j < nslots) {
+                int kp, ghost;
+                plane_of(j, kp, ghost);
+                mbar_wait(bar_eempty + 8 * issue.stage, issue.phase ^ 1u);  // the H-warps are done with this stage
+                const unsigned st = sE + issue.stage * ESTAGE;
+                if (ghost) {  // (patch mode) the whole tile by software copies
+                    soft_fill(st, kp, ghost, true);
+                    cp_async_mbar_arrive_noinc(bar_efull + 8 * issue.stage);
+                    if (lane == 0) mbar_arrive(bar_tma + 8 * issue.stage);  // (no TMA copy for this slot: keep the barrier's phase in step)
+                } else if (lane == 0) {
+                    const unsigned bar = patch ? bar_tma + 8 * issue.stage : bar_efull + 8 * issue.stage;
+                    if (patch) fence_proxy_async();
+                    mbar_arrive_expect_tx(bar, 3 * ECOMP * ES);
+                    tma_load_3d(st, &P.tm[0], bar, 2 * ex0, ey0, kp);
+                    tma_load_3d(st + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp);
+                    tma_load_3d(st + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp);
+                }
+                issue.advance<SE>();
             }
         }
         cp_async_wait<0>();

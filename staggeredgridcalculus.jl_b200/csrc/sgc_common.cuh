@@ -111,6 +111,30 @@ inline cplx cinv_host(cplx w) {
     return cplx{p * s, q * s};
 }
 
+// Julia inv(::ComplexF64) for device code (the same scaled robust algorithm as cinv_host, multiply-add not fused).
+SGC_HD cplx cinv(cplx w) {
+    double c = w.re, d = w.im;
+    const double absc = fabs(c), absd = fabs(d);
+    const double cd = absc > absd ? absc : absd;
+    const double eps = 2.220446049250313e-16;
+    const double bs = 2.0 / (eps * eps);
+    double s = 1.0;
+    if (cd >= 1.7976931348623157e308 / 2) { c *= 0.5; d *= 0.5; s = 0.5; }
+    else if (cd <= 2 * 2.2250738585072014e-308 / eps) { c *= bs; d *= bs; s = bs; }
+    double p, q;
+    if (absd <= absc) {
+        const double r = d / c;
+        p = 1.0 / (d * r + c);
+        q = -r * p;
+    } else {
+        const double cc = -d, dd = -c;
+        const double r = dd / cc;
+        const double pp = 1.0 / (dd * r + cc);
+        q = pp; p = -r * pp;
+    }
+    return cplx{p * s, q * s};
+}
+
 // ---- streaming memory access ------------------------------------------------------------------
 // Fields are read once per kernel and written once: keep them out of L1 (no_allocate) and let
 // the 126 MB L2 provide the halo reuse between neighbouring CTAs.

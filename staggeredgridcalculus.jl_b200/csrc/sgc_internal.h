@@ -112,6 +112,7 @@ struct Term {
     bool cc;          // coefficient tables are complex
     size_t off_c, off_w;  // offsets of the tables in the arena (bytes); w unused unless weighted
     sgc::cplx a2, a1, b0, w_hi, w_lo;  // scalars (stored as complex; narrowed when !cc)
+    HV al;            // parity·α of a ∂ term (sgc_op_set_axes rebuilds the table c[i] = al·∆w⁻¹[i] on the device)
 };
 
 struct sgc_op {

@@ -194,6 +194,7 @@ static int add_term(sgc_op *op, OpBuilder &b, int kind, int out, int in, int axi
     Term t{};
     t.out = out; t.in = in; t.kind = kind; t.axis = axis; t.fwd = isfwd ? 1 : 0; t.bloch = isbloch ? 1 : 0;
     t.e = to_cplx(ev); t.e_real = ev.cx ? 0 : 1; t.cc = cc;
+    t.al = al;
     std::vector<HV> c(Nw), w;
     if (kind == KIND_PARTIAL) {
         for (int64_t i = 0; i < Nw; ++i) c[i] = hmul(al, vec_at(v1, coef_complex, i));  // (α * ∆w⁻¹[i])

@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["Grid", "PMLParam", "calc_sfactor", "create_stretched_dl", "invert_dl", "graded_lprim"]
+__all__ = ["Grid", "PMLParam", "calc_sfactor", "create_stretched_dl", "invert_dl", "graded_lprim", "pml_loc", "DeviceAxes"]
 
 
 class Grid:
@@ -72,6 +72,70 @@ def create_stretched_dl(omega, grid: Grid, Npml, pml: PMLParam | None = None):
                     s[i] = calc_sfactor(omega, ri - lpml_p, Lp, pml)
             out[ngt].append(s * grid.dl[ngt][k])
     return out
+
+
+def pml_loc(grid: Grid, Npml):
+    """`pml_loc` — src/pml.jl:165-174: ((lpml₋[k]), (lpml₊[k])), ((Lpml₋[k]), (Lpml₊[k]))."""
+    lp_n, lp_p, L_n, L_p = [], [], [], []
+    for k in range(len(grid.N)):
+        lprim = grid.l[0][k]
+        full = np.concatenate([lprim, [grid.bounds[1][k]]])
+        nn, npos = int(Npml[0][k]), int(Npml[1][k])
+        a = full[nn]
+        b = grid.bounds[1][k] if npos == 0 else lprim[len(lprim) - npos]
+        lp_n.append(a); lp_p.append(b)
+        L_n.append(a - grid.bounds[0][k]); L_p.append(grid.bounds[1][k] - b)
+    return (lp_n, lp_p), (L_n, L_p)
+
+
+class DeviceAxes:
+    """The per-axis vectors of a Grid with PML, produced ON THE DEVICE (`sgc_axis_*`, csrc/sgc_grid.cu): `stretch(ω)`
+    gives s∆l / (s∆l)⁻¹ as device tensors, `refresh(op, ω)` rebuilds an operator handle's coefficient tables for a new
+    ω without a host round-trip (frequency sweeps).  `which` = 0 for the primal set (∆l at primal points), 1 dual."""
+
+    def __init__(self, grid: Grid, Npml, which: int, pml: "PMLParam | None" = None):
+        import ctypes as C
+        from ._lib import lib, check
+        self._lib, self._check, self._C = lib, check, C
+        (lp_n, lp_p), (L_n, L_p) = pml_loc(grid, Npml)
+        par = None
+        if pml is not None:
+            par = (C.c_double * 5)(pml.m, pml.R, pml.kmax, pml.amax, pml.ma)
+        self.h, self.n = [], []
+        for k in range(len(grid.N)):
+            l = np.ascontiguousarray(grid.l[which][k], dtype=np.float64)
+            dl = np.ascontiguousarray(grid.dl[which][k], dtype=np.float64)
+            h = C.c_void_p()
+            check(lib.sgc_axis_create(C.byref(h), len(l), l.ctypes.data_as(C.POINTER(C.c_double)), dl.ctypes.data_as(C.POINTER(C.c_double)),
+                                      float(lp_n[k]), float(lp_p[k]), float(L_n[k]), float(L_p[k]), par))
+            self.h.append(h)
+            self.n.append(len(l))
+
+    def stretch(self, omega, stream=None):
+        """[(s∆l_k, (s∆l_k)⁻¹) for every axis k] as complex128 device tensors."""
+        import torch
+        from .device import stream_handle
+        C = self._C
+        out = []
+        for h, n in zip(self.h, self.n):
+            a = torch.empty(n, dtype=torch.complex128, device="cuda")
+            b = torch.empty(n, dtype=torch.complex128, device="cuda")
+            self._check(self._lib.sgc_axis_stretch(h, float(omega), C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), stream_handle(stream)))
+            out.append((a, b))
+        return out
+
+    def refresh(self, op, omega, stream=None):
+        from .device import stream_handle
+        C = self._C
+        arr = (C.c_void_p * len(self.h))(*[h.value for h in self.h])
+        self._check(self._lib.sgc_op_set_axes(op._h, arr, float(omega), stream_handle(stream)))
+
+    def __del__(self):
+        try:
+            for h in self.h:
+                self._lib.sgc_axis_destroy(h)
+        except Exception:
+            pass
 
 
 def invert_dl(dl):

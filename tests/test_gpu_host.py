@@ -115,3 +115,45 @@ def test_host_registration_follows_array_lifetime(S):
         assert_parity(G, ref, "apply_host after re-allocation", exact=True)
         del F, G
         gc.collect()
+
+
+def test_device_pml_vectors_and_operator_refresh(S):
+    """s∆l / (s∆l)⁻¹ produced on the device (`sgc_axis_stretch`) against the host restatement of
+    create_stretched_∆l / invert_∆l (gridgen.py; src/pml.jl:94-153, src/util.jl:42-48) within 4 ulp, and an operator
+    whose tables were rebuilt on the device for a new ω (`sgc_op_set_axes`) against one created from the host vectors."""
+    from sgc_b200 import gridgen as GG
+    rng = np.random.default_rng(70)
+    N = (48, 40, 36)
+    lprim = [GG.graded_lprim(n, rng) for n in N]
+    for isbloch in ([False] * 3, [True, False, True]):
+        grid = GG.Grid(lprim, isbloch)
+        Npml = ([6, 5, 0], [4, 6, 7])
+        for which in (0, 1):
+            axes = GG.DeviceAxes(grid, Npml, which)
+            for omega in (2 * np.pi / 9.3, 0.37):
+                sdl = GG.create_stretched_dl(omega, grid, Npml)
+                inv = GG.invert_dl(sdl)
+                got = axes.stretch(omega)
+                for k in range(3):
+                    assert_parity(got[k][0].cpu().numpy(), sdl[which][k], f"s∆l axis {k} set {which} ω={omega:.3f}")
+                    assert_parity(got[k][1].cpu().numpy(), inv[which][k], f"(s∆l)⁻¹ axis {k} set {which} ω={omega:.3f}")
+            # operator refresh: create at ω₀, rebuild on the device for ω₁, compare with an operator created at ω₁
+            w0, w1 = 0.5, 2 * np.pi / 7.1
+            isfwd = [True, False, True]
+            e = [np.exp(-0.3j), 1.0, np.exp(0.9j)]
+            inv0 = GG.invert_dl(GG.create_stretched_dl(w0, grid, Npml))[which]
+            inv1 = [t[1].cpu().numpy() for t in axes.stretch(w1)]
+            F = rand_field(rng, N + (3,), True)
+            for maker in (lambda d: S.Operator.curl(S.SGC_C128, N, isfwd, d, isbloch, e, alpha=0.5 - 0.25j),
+                          lambda d: S.Operator.divg(S.SGC_C128, N, isfwd, d, isbloch, e),
+                          lambda d: S.Operator.grad(S.SGC_C128, N, isfwd, d, isbloch, e, alpha=-2.0)):
+                o = maker(inv0)
+                axes.refresh(o, w1)
+                ref = maker(inv1)
+                nout, nin = o.n_out, o.n_in
+                Fd = S.DeviceArray.from_numpy(F if nin == 3 else np.asfortranarray(F[..., 0]))
+                shp = N + (3,) if nout == 3 else N
+                G1, G2 = S.DeviceArray.zeros(shp), S.DeviceArray.zeros(shp)
+                o.apply(G1, Fd, "=")
+                ref.apply(G2, Fd, "=")
+                assert_parity(G1.numpy(), G2.numpy(), "operator refreshed on the device vs created from the same vectors", exact=True)
