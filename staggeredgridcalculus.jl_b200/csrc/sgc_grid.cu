@@ -11,6 +11,8 @@
 
 #include <cmath>
 
+#include "sgc_kernels.cuh"
+
 using namespace sgc;
 
 struct sgc_axis {
