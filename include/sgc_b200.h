@@ -57,6 +57,9 @@ extern "C" {
 /* library / device plumbing                                                                */
 /* ---------------------------------------------------------------------------------------- */
 int sgc_abi_version(void);
+/* bit 0: development build with every tile / ring-depth variant of the tuning sweeps (`make EXTRA=-DSGC_SWEEP_BUILD`);
+ * the product library carries the defaults and a few alternatives only. */
+int sgc_build_flags(void);
 const char *sgc_last_error(void);
 int sgc_device_count(int *count);
 int sgc_set_device(int device);
@@ -399,8 +402,17 @@ int sgc_asm_fill_host(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowv
 
 int sgc_asm_destroy(sgc_asm *a);
 
-/* y = A·x for an assembled CSC matrix on the device (the cross-check `mul!(g, Curl, f)` of
- * test/curl.jl:55).  One thread per column, atomics on y; test utility, not a tuned SpMV. */
+/* y = A·x for an assembled CSC matrix on the device: `mul!(g, Curl, f)` (test/curl.jl:55, test/partial.jl:67-70).
+ * Plan form (the tuned one): sgc_spmv_create sorts the entries by row once (stable radix sort: within a row the
+ * columns stay ascending, the order of Julia's column sweep) and keeps, per row, the positions of its entries in the
+ * CSC arrays and their columns; sgc_spmv_apply is then a row-parallel gather without atomics, which may be repeated
+ * with new nzval / x.  colptr / rowval are only read during creation.  Dimensions and nnz must fit 32 bits. */
+typedef struct sgc_spmv sgc_spmv;
+int sgc_spmv_create(sgc_spmv **plan, int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval, int index_base,
+                    void *stream);
+int sgc_spmv_apply(const sgc_spmv *plan, const void *nzval, int val_dtype, const void *x, void *y, void *stream);
+int sgc_spmv_destroy(sgc_spmv *plan);
+/* One-shot column-parallel form (one thread per column, atomics on y): no plan, slower. */
 int sgc_csc_matvec(int64_t m, int64_t n, const int64_t *colptr, const int64_t *rowval,
                    const void *nzval, int index_base, int val_dtype, const void *x, void *y,
                    void *stream);

@@ -42,6 +42,7 @@ vpp = C.POINTER(C.c_void_p)
 
 _PROTOS = {
     "sgc_abi_version": (C.c_int, []),
+    "sgc_build_flags": (C.c_int, []),
     "sgc_last_error": (C.c_char_p, []),
     "sgc_device_count": (C.c_int, [intp]),
     "sgc_set_device": (C.c_int, [C.c_int]),
@@ -142,6 +143,9 @@ _PROTOS = {
     "sgc_asm_nnz_host": (C.c_int, [C.c_void_p, i64p]),
     "sgc_asm_fill_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "sgc_asm_destroy": (C.c_int, [C.c_void_p]),
+    "sgc_spmv_create": (C.c_int, [vpp, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "sgc_spmv_apply": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "sgc_spmv_destroy": (C.c_int, [C.c_void_p]),
     "sgc_csc_matvec": (C.c_int, [C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_void_p]),
 }

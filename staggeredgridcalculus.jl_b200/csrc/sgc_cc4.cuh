@@ -1,27 +1,33 @@
-// sgc_cc4.cuh — fused curl-of-curl, fourth generation: TMA-fed, warp-specialised, mbarrier-pipelined (sm_100a).
+// sgc_cc4.cuh — fused curl-of-curl, fourth generation (EXPERIMENT, opt-in): TMA-fed, warp-specialised,
+// mbarrier-pipelined (sm_100a).  Selected with kernel version 4 (sgc_op_set_tuning); not the default.
 //
 // Same mathematics as k_curlcurl3w (sgc_curlcurl.cuh): G OP C₂(C₁ F) with H = C₁ F living only in shared memory,
 // every value produced by the arithmetic of two apply_curl! calls (matrixfree/differential/curl.jl:52-137), so the
-// result is bit-identical to the two-pass path.  What changed is how the SM is kept busy.  The ncu source page of the
-// third generation (profiles/r2_cc3w_source_summary.txt) showed 497 thread-instructions per cell of which 132 are the
-// FP64 arithmetic, issue slots 46 % busy at 16 warps/SM behind one __syncthreads per plane, and the LDGSTS
-// (cp.async) copies costing 16 shared-memory wavefronts per warp request instead of 4.  Here:
+// result is bit-identical to the two-pass path (tests/test_gpu_matrixfree.py).  The ncu source page of the third
+// generation (profiles/r2_cc3w_source_summary.txt) showed 497 thread-instructions per cell of which 132 are the FP64
+// arithmetic, issue slots 46 % busy at 16 warps/SM behind one __syncthreads per plane, and the LDGSTS (cp.async)
+// copies costing 15 shared-memory wavefronts per warp request instead of 4.  This kernel attacks exactly that:
 //
 //   * one PRODUCER warp feeds an SE-stage ring of E planes with `cp.async.bulk.tensor` (TMA): one elected lane issues
 //     three 3-D box copies per plane — (TX+2)×(TY+2) elements of Ex, Ey, Ez — that land in shared memory as whole
 //     lines and complete on an mbarrier (`complete_tx`); out-of-range box cells are zero-filled by the copy engine,
 //     which is exactly what a symmetric (PEC/PMC) boundary discards anyway.  No thread computes a load address.
 //   * TY+2 H-WARPS turn E planes into H planes (one tile row each, the last one the extra tile column) and TY
-//     D-WARPS turn H planes into output planes.  Each warp runs one short straight loop; the two groups are coupled
-//     only by mbarriers per ring stage (E full/empty, H full/empty), so there is no CTA-wide barrier at all and the
-//     H-warps run ahead of the D-warps by up to the ring depth.
-//   * one CTA per SM (2·TY+3 warps), z-march long enough that the two extra E planes per CTA are ≤ 3 %.
+//     D-WARPS turn H planes into output planes; the two groups are coupled only by mbarriers per ring stage
+//     (E full/empty, H full/empty): no CTA-wide barrier at all.
+//   * one CTA per SM (2·TY+3 warps).
 //
-// Tiles that need data the copy engine cannot fetch — Bloch wrap-around columns / rows of edge tiles, the
-// neighbours' ghost planes of a z-slab — run in PATCH mode: the TMA copy of a plane signals a second barrier, and
-// the 32 producer lanes overwrite the out-of-range cells with `cp.async` copies from the wrapped positions (ghost
-// planes: the whole tile), each lane joining the plane's "full" barrier through `cp.async.mbarrier.arrive.noinc`,
-// so the patch copies are pipelined like everything else.
+// Measured (B200, 256³ ComplexF64, PEC box, profiles/r2_sweep_cc4*.jsonl): 0.484 ms at TY = 6 (15 warps, 128
+// registers), 0.543 ms at TY = 8 (19 warps, 96 registers + spills) — against 0.472 ms for the third generation and
+// 0.530 ms for two k_curl3p launches.  The ncu source page (profiles/r2_cc4_source_summary.txt) says why it does not
+// win: H- and D-warps are released by the same barrier events, so all warps of an SM run their FP64 phase at the same
+// time (the FP64 pipe is saturated for ≈ 30 % of a plane period and idle for the rest) and their barrier / shared-
+// memory latency phases at the same time; 27 % of all stall samples sit on mbarrier try-waits.  Fetching the next
+// plane's operands ahead of the arithmetic (software pipelining inside each warp) made it slower (0.67 ms: the
+// doubled operand set spills), as did running the two curls per z-chunk so that H is re-read from L2
+// (tools/time_l2_chunked.py: 0.57–0.97 ms).  Kept as a working, bit-identical TMA / mbarrier reference for the next
+// attempt (two CTAs per SM, or H- and D-groups a half period apart); Bloch x / y boundaries and z-slab ghost planes
+// are not handled here — the launcher routes those to the third generation.
 #pragma once
 #include <cuda.h>
 
@@ -71,12 +77,6 @@ SGC_D void tma_load_3d(unsigned dst, const CUtensorMap *tm, unsigned bar, int c0
 SGC_D void tma_prefetch_desc(const CUtensorMap *tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
-SGC_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// joins the barrier when all cp.async copies this thread has issued so far have landed (no extra pending count)
-SGC_D void cp_async_mbar_arrive_noinc(unsigned bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
-}
-
 // ring position: stage index and the parity of the phase a waiter expects
 struct RingPos {
     int stage;
@@ -137,8 +137,8 @@ __global__ void __launch_bounds__(32 * (2 * TY + 3), 1) k_cc4(const __grid_const
     const unsigned sE = ((unsigned)__cvta_generic_to_shared(sgc_smem_raw) + 127u) & ~127u;
     const unsigned sH = sE + SE * ESTAGE;
     const unsigned bars = sH + SH * HSTAGE;
-    const unsigned bar_efull = bars, bar_eempty = bars + 8 * SE, bar_tma = bars + 16 * SE;
-    const unsigned bar_hfull = bars + 24 * SE, bar_hempty = bar_hfull + 8 * SH;
+    const unsigned bar_efull = bars, bar_eempty = bars + 8 * SE;
+    const unsigned bar_hfull = bars + 16 * SE, bar_hempty = bar_hfull + 8 * SH;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz;
@@ -160,18 +160,10 @@ __global__ void __launch_bounds__(32 * (2 * TY + 3), 1) k_cc4(const __grid_const
     const int eb = hb + min(0, s1z);
     const int nslots = n + 2;  // E slots 0 … n+1 ↔ planes eb … eb+n+1
 
-    // PATCH mode (uniform per CTA): the tile reaches over an x / y edge on an axis that wraps around, or the march
-    // touches a plane that lives behind a ghost pointer
-    const bool x_out = (ex0 < 0) || (ex0 + EX > Nx), y_out = (ey0 < 0) || (ey0 + EY > Ny);
-    const bool x_wraps = p.bc1_lo[0] == BC_BLOCH || p.bc2_lo[0] == BC_BLOCH, y_wraps = p.bc1_lo[1] == BC_BLOCH || p.bc2_lo[1] == BC_BLOCH;
-    const bool ghost_touch = (lo_ext && eb < 0) || (hi_ext && eb + nslots > Nz);
-    const bool patch = (x_out && x_wraps) || (y_out && y_wraps) || ghost_touch;
-
     if (threadIdx.x == 0) {
         for (int s = 0; s < SE; ++s) {
-            mbar_init(bar_efull + 8 * s, patch ? 32u : 1u);
+            mbar_init(bar_efull + 8 * s, 1u);
             mbar_init(bar_eempty + 8 * s, W_H);
-            mbar_init(bar_tma + 8 * s, 1u);
         }
         for (int s = 0; s < SH; ++s) {
             mbar_init(bar_hfull + 8 * s, W_H);
@@ -184,69 +176,20 @@ __global__ void __launch_bounds__(32 * (2 * TY + 3), 1) k_cc4(const __grid_const
     if (warp == 0) {
         // ======================================= PRODUCER ===========================================================
         if (lane == 0) { tma_prefetch_desc(&P.tm[0]); tma_prefetch_desc(&P.tm[1]); tma_prefetch_desc(&P.tm[2]); }
-        constexpr int LAG = SE - 1;  // patch copies of slot j are issued when the TMA copy of slot j + LAG goes out
-        RingPos issue{0, 0}, fix{0, 0};
-        // is slot j a ghost plane, a local plane (possibly wrapped in z)?  returns the source plane / pointers
-        auto plane_of = [&](int j, int &kp, int &ghost) {
-            const int ke = eb + j;
-            ghost = 0;
-            if (ke >= 0 && ke < Nz) kp = ke;
-            else if (ke < 0 && lo_ext) { ghost = 1; kp = 0; }
-            else if (ke >= Nz && hi_ext) { ghost = 2; kp = 0; }
-            else kp = wrap_index(ke, Nz);
-        };
-        // software copy of the tile cells the copy engine cannot fetch (all == whole tile) into stage st
-        auto soft_fill = [&](unsigned st, int kp, int ghost, bool all) {
-            const T *s0, *s1, *s2;
-            if (ghost == 1) { s0 = p.ghost_lo[0]; s1 = p.ghost_lo[1]; s2 = p.ghost_lo[2]; }
-            else if (ghost == 2) { s0 = p.ghost_hi[0]; s1 = p.ghost_hi[1]; s2 = p.ghost_hi[2]; }
-            else { const int64_t off = (int64_t)kp * sz; s0 = p.F[0] + off; s1 = p.F[1] + off; s2 = p.F[2] + off; }
-            for (int q = lane; q < ECOMP; q += 32) {
-                const int py = q / EX, px = q - py * EX;
-                const int gx = ex0 + px, gy = ey0 + py;
-                const bool oob = gx < 0 || gx >= Nx || gy < 0 || gy >= Ny;
-                if (all || oob) {
-                    const int64_t g = (int64_t)wrap_index(gy, Ny) * sy + wrap_index(gx, Nx);
-                    const unsigned d = st + (unsigned)(q * ES);
-                    cp_async_to(d, s0 + g);
-                    cp_async_to(d + ECB, s1 + g);
-                    cp_async_to(d + 2 * ECB, s2 + g);
-                }
-            }
-        };
-        for (int j = 0; j < nslots + (patch ? LAG : 0); ++j) {
-            // (patch first: the H-warps free the stage slot j wants only after slot j − SE + 1 — patched here — is full)
-            if (patch && j >= LAG) {
-                int kp, ghost;
-                plane_of(j - LAG, kp, ghost);
-                if (!ghost) {
-                    mbar_wait(bar_tma + 8 * fix.stage, fix.phase);  // the zero-filled box has landed: now overwrite
-                    soft_fill(sE + fix.stage * ESTAGE, kp, 0, false);
-                    cp_async_mbar_arrive_noinc(bar_efull + 8 * fix.stage);
-                }
-                fix.advance<SE>();
-            }
-            if (j < nslots) {
-                int kp, ghost;
-                plane_of(j, kp, ghost);
+        if (lane == 0) {
+            RingPos issue{0, 0};
+            for (int j = 0; j < nslots; ++j) {
+                const int kp = wrap_index(eb + j, Nz);  // (a plane beyond a Bloch z face wraps around; beyond a symmetric face it is never used)
                 mbar_wait(bar_eempty + 8 * issue.stage, issue.phase ^ 1u);  // the H-warps are done with this stage
                 const unsigned st = sE + issue.stage * ESTAGE;
-                if (ghost) {  // (patch mode) the whole tile by software copies
-                    soft_fill(st, kp, ghost, true);
-                    cp_async_mbar_arrive_noinc(bar_efull + 8 * issue.stage);
-                    if (lane == 0) mbar_arrive(bar_tma + 8 * issue.stage);  // (no TMA copy for this slot: keep the barrier's phase in step)
-                } else if (lane == 0) {
-                    const unsigned bar = patch ? bar_tma + 8 * issue.stage : bar_efull + 8 * issue.stage;
-                    if (patch) fence_proxy_async();
-                    mbar_arrive_expect_tx(bar, 3 * ECOMP * ES);
-                    tma_load_3d(st, &P.tm[0], bar, 2 * ex0, ey0, kp);
-                    tma_load_3d(st + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp);
-                    tma_load_3d(st + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp);
-                }
+                const unsigned bar = bar_efull + 8 * issue.stage;
+                mbar_arrive_expect_tx(bar, 3 * ECOMP * ES);
+                tma_load_3d(st, &P.tm[0], bar, 2 * ex0, ey0, kp);
+                tma_load_3d(st + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp);
+                tma_load_3d(st + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp);
                 issue.advance<SE>();
             }
         }
-        cp_async_wait<0>();
         return;
     }
 

@@ -103,21 +103,26 @@ static int launch_curl3p_tiles(const CurlParams<T, C> &p, int tx, int ty, int st
     if (tx == TX && ty == TY && stages == S && minb == MINB)                                                   \
         return xshfl ? launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, true>(p, grid, st)                        \
                      : launch_curl3p_one<T, C, ADD, TX, TY, S, MINB, false>(p, grid, st);
-    CURLP_CASE(32, 4, 4, 4)
-    CURLP_CASE(32, 4, 5, 4)
+    // the product library carries the default (32x4 tiles, 6-stage ring) and three alternatives; the full tile /
+    // ring-depth / occupancy matrix of the round-1 sweeps (profiles/r1_sweep_curl_256*.jsonl) builds with
+    // `make EXTRA=-DSGC_SWEEP_BUILD`
     CURLP_CASE(32, 4, 6, 4)
+    CURLP_CASE(32, 4, 4, 4)
+    CURLP_CASE(32, 8, 4, 3)
+    CURLP_CASE(64, 4, 4, 3)
+#ifdef SGC_SWEEP_BUILD
+    CURLP_CASE(32, 4, 5, 4)
     CURLP_CASE(32, 4, 7, 4)
     CURLP_CASE(32, 4, 8, 3)
     CURLP_CASE(32, 4, 3, 4)
     CURLP_CASE(32, 8, 3, 3)
-    CURLP_CASE(32, 8, 4, 3)
     CURLP_CASE(32, 8, 4, 2)
     CURLP_CASE(32, 8, 6, 2)
     CURLP_CASE(32, 16, 3, 2)
     CURLP_CASE(32, 16, 4, 1)
-    CURLP_CASE(64, 4, 4, 3)
     CURLP_CASE(64, 4, 4, 2)
     CURLP_CASE(64, 8, 3, 2)
+#endif
 #undef CURLP_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl: tile %dx%d, %d stages, %d CTAs/SM is not built", tx, ty, stages, minb);
 }
@@ -126,11 +131,13 @@ template <typename T, typename C, bool ADD>
 static void launch_curl3_tiles(const CurlParams<T, C> &p, int tx, int ty, dim3 grid, cudaStream_t st) {
 #define CURL_CASE(TX, TY) \
     if (tx == TX && ty == TY) { k_curl3<T, C, ADD, TX, TY><<<grid, dim3(TX, TY, 1), 0, st>>>(p); return; }
-    CURL_CASE(32, 4)
     CURL_CASE(32, 8)
+#ifdef SGC_SWEEP_BUILD
+    CURL_CASE(32, 4)
     CURL_CASE(32, 16)
     CURL_CASE(64, 4)
     CURL_CASE(64, 8)
+#endif
 #undef CURL_CASE
     k_curl3<T, C, ADD, 32, 8><<<dim3((p.Nx + 31) / 32, (p.Ny + 7) / 8, grid.z), dim3(32, 8, 1), 0, st>>>(p);
 }

@@ -65,11 +65,8 @@ int launch_cc4_dirs(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
 template <typename C, bool ADD>
 int launch_cc4_tiles(const CurlCurl4Params<C> &P, int ty, int se, int sh, dim3 grid, cudaStream_t st) {
 #define CC4_CASE(TY, SE, SH) if (ty == TY && se == SE && sh == SH) return launch_cc4_dirs<C, ADD, TY, SE, SH>(P, grid, st);
-    CC4_CASE(8, 4, 3)
-    CC4_CASE(8, 5, 4)
     CC4_CASE(6, 4, 3)
-    CC4_CASE(10, 4, 3)
-    CC4_CASE(12, 4, 3)
+    CC4_CASE(8, 4, 3)
 #undef CC4_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (TMA): tile 32x%d with %d/%d stages is not built", ty, se, sh);
 }
@@ -108,8 +105,10 @@ int launch_cc_tiles(const CurlCurlParams<T, C> &p, int tx, int ty, int se, dim3 
 #define CC_CASE(TX, TY, SE, MINB) \
     if (tx == TX && ty == TY && se == SE) return launch_cc_one<T, C, ADD, TX, TY, SE, MINB>(p, grid, st);
     CC_CASE(32, 8, 3, 2)
+#ifdef SGC_SWEEP_BUILD
     CC_CASE(32, 4, 4, 3)
     CC_CASE(64, 4, 3, 2)
+#endif
 #undef CC_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl: tile %dx%d with %d stages is not built", tx, ty, se);
 }
@@ -134,11 +133,13 @@ int launch_ccw_dirs(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
 template <typename T, typename C, bool ADD>
 int launch_ccw_tiles(const CurlCurlParams<T, C> &p, int ty, int se, dim3 grid, cudaStream_t st) {
 #define CCW_CASE(TY, SE) if (ty == TY && se == SE) return launch_ccw_dirs<T, C, ADD, TY, SE>(p, grid, st);
-    CCW_CASE(8, 3)
     CCW_CASE(7, 3)
     CCW_CASE(7, 4)
-    CCW_CASE(4, 3)
     CCW_CASE(4, 4)
+#ifdef SGC_SWEEP_BUILD
+    CCW_CASE(8, 3)
+    CCW_CASE(4, 3)
+#endif
 #undef CCW_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl: tile 32x%d with %d stages is not built", ty, se);
 }
@@ -194,29 +195,24 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
     dim3 grid((unsigned)((p.Nx + tx - 1) / tx), (unsigned)((p.Ny + ty - 1) / ty), (unsigned)((nk + p.march - 1) / p.march));
     if (grid.y > 65535 || grid.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
     if ((int64_t)p.Nx * p.Ny >= (int64_t)0x7fffffff) return sgc_fail(SGC_ERR_INVALID, "plane too large for the fused curl-of-curl");
-    // default for ComplexF64 fields on grids that hold a whole tile: the TMA-fed warp-specialised kernel (variant 2 / 1
-    // select the third / first generation)
+    // version 4: the TMA-fed warp-specialised experiment (sgc_cc4.cuh) where it applies — ComplexF64 fields, a grid that
+    // holds a whole tile, no Bloch wrap in x / y and no slab ghost planes (the copy engine cannot fetch those cells);
+    // everything else, and version 4 where it does not apply, runs the third generation
     if constexpr (std::is_same<T, cplx>::value) {
-        // version 0: automatic (tuning knobs that do not name a built configuration fall back to the defaults);
-        // version 4: as given (an unbuilt configuration is an error)
-        auto built = [](int ty, int se, int sh) {
-            return (ty == 8 && ((se == 4 && sh == 3) || (se == 5 && sh == 4))) || ((ty == 6 || ty == 10 || ty == 12) && se == 4 && sh == 3);
-        };
-        int ty4 = c2->tile_y ? c2->tile_y : 8;
-        int se4 = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 4;
-        int sh4 = ((c2->variant >> 8) & 0xF) ? ((c2->variant >> 8) & 0xF) : 3;
-        if (version == 0 && !built(ty4, se4, sh4)) { ty4 = 8; se4 = 4; sh4 = 3; }
-        if ((version == 0 || version == 4) && p.Nx >= 34 && p.Ny >= ty4 + 2 && ((uintptr_t)F % 16 == 0)) {
+        int ty4 = (c2->tile_y == 8) ? 8 : 6;
+        const bool wraps_xy = a1.bloch[0] || a1.bloch[1] || a2.bloch[0] || a2.bloch[1];
+        const bool ghosts = (ghost_lo && ghost_lo[0]) || (ghost_hi && ghost_hi[0]) || c1->lo_iface || c1->hi_iface;
+        if (version == 4 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= ty4 + 2) {
             CurlCurl4Params<C> P{};
             P.q = p;
             int s4 = SGC_OK;
             for (int d = 0; d < 3 && !s4; ++d) s4 = encode_component(&P.tm[d], p.F[d], p.Nx, p.Ny, p.Nz, 34, ty4 + 2);
             if (!s4) {
                 const int64_t tiles = (int64_t)((p.Nx + 31) / 32) * ((p.Ny + ty4 - 1) / ty4);
-                P.q.march = (c2->march > 0 && version == 4) ? c2->march : cc4_march(tiles, nk);
+                P.q.march = c2->march > 0 ? c2->march : cc4_march(tiles, nk);
                 dim3 g4((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty4 - 1) / ty4), (unsigned)((nk + P.q.march - 1) / P.q.march));
                 if (g4.y > 65535 || g4.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
-                s4 = add_mode ? launch_cc4_tiles<C, true>(P, ty4, se4, sh4, g4, st) : launch_cc4_tiles<C, false>(P, ty4, se4, sh4, g4, st);
+                s4 = add_mode ? launch_cc4_tiles<C, true>(P, ty4, 4, 3, g4, st) : launch_cc4_tiles<C, false>(P, ty4, 4, 3, g4, st);
                 if (s4) return s4;
                 return sgc_check_launch("k_cc4");
             }
@@ -224,6 +220,14 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
         }
     }
     int s;
+    if (version == 4) {  // k_cc4 asked for but not applicable (Float64 field, tiny grid): third generation with its own defaults
+        const int ty3 = 7, se3 = sizeof(T) == 8 ? 4 : 3;
+        p.march = nk >= 256 ? 64 : 32;
+        dim3 g3((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty3 - 1) / ty3), (unsigned)((nk + p.march - 1) / p.march));
+        s = add_mode ? launch_ccw_tiles<T, C, true>(p, ty3, se3, g3, st) : launch_ccw_tiles<T, C, false>(p, ty3, se3, g3, st);
+        if (s) return s;
+        return sgc_check_launch("k_curlcurl3");
+    }
     if (version == 1) s = add_mode ? launch_cc_tiles<T, C, true>(p, tx, ty, se, grid, st) : launch_cc_tiles<T, C, false>(p, tx, ty, se, grid, st);
     else s = add_mode ? launch_ccw_tiles<T, C, true>(p, ty, se, grid, st) : launch_ccw_tiles<T, C, false>(p, ty, se, grid, st);
     if (s) return s;

@@ -39,6 +39,13 @@ int sgc_check_launch(const char *what) {
 void sgc_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int sgc_abi_version(void) { return SGC_ABI_VERSION; }
+extern "C" int sgc_build_flags(void) {
+#ifdef SGC_SWEEP_BUILD
+    return 1;
+#else
+    return 0;
+#endif
+}
 extern "C" const char *sgc_last_error(void) { return g_err.c_str(); }
 extern "C" int64_t sgc_launch_count(void) { return g_launches.load(); }
 

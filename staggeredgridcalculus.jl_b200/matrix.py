@@ -58,8 +58,32 @@ class DeviceCSC:
         cp, rv, nz = self.to_host()
         np.savez(path, m=self.m, n=self.n, index_base=self.index_base, colptr=cp, rowval=rv, nzval=nz)
 
+    def mul(self, x: torch.Tensor, y: "torch.Tensor | None" = None) -> torch.Tensor:
+        """`mul!(y, A, x)` on the device through the row-sorted plan (`sgc_spmv_*`): the plan is built on first use and
+        kept; every product is a gather without atomics, accumulated per row in ascending column order."""
+        code = _lib.SGC_C128 if self.nzval.dtype == torch.complex128 else _lib.SGC_F64
+        if getattr(self, "_plan", None) is None:
+            h = C.c_void_p()
+            check(lib.sgc_spmv_create(C.byref(h), self.m, self.n, C.c_void_p(self.colptr.data_ptr()), C.c_void_p(self.rowval.data_ptr()),
+                                      self.index_base, stream_handle()))
+            self._plan = h
+        x = x.to(self.nzval.dtype).contiguous()
+        if y is None:
+            y = torch.empty(self.m, dtype=self.nzval.dtype, device=x.device)
+        check(lib.sgc_spmv_apply(self._plan, C.c_void_p(self.nzval.data_ptr()), code, C.c_void_p(x.data_ptr()), C.c_void_p(y.data_ptr()),
+                                 stream_handle()))
+        return y
+
+    def __del__(self):
+        try:
+            if getattr(self, "_plan", None) is not None:
+                lib.sgc_spmv_destroy(self._plan)
+                self._plan = None
+        except Exception:
+            pass
+
     def matvec(self, x: torch.Tensor) -> torch.Tensor:
-        """`A * x` on the device (test utility; the reference's cross-check `mul!(g, A, f)`)."""
+        """`A * x` on the device, column-parallel with atomics (no plan; the reference's cross-check `mul!(g, A, f)`)."""
         code = _lib.SGC_C128 if self.nzval.dtype == torch.complex128 else _lib.SGC_F64
         x = x.to(self.nzval.dtype).contiguous()
         y = torch.empty(self.m, dtype=self.nzval.dtype, device=x.device)

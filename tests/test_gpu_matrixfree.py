@@ -213,10 +213,24 @@ def test_apply_curl_dtypes_and_alpha(S, cplx_field, cplx_coef, alpha):
 # every instantiated configuration of the fused kernels: (tile_x, tile_y, stages, CTAs/SM) of the
 # cp.async ring kernel (variant 0) with shuffle / shared-memory x-neighbours, and the
 # register-prefetch kernel (variant 1)
-RING_CONFIGS = [(32, 4, 4, 4), (32, 4, 3, 4), (32, 4, 5, 4), (32, 4, 6, 4), (32, 4, 7, 4), (32, 4, 8, 3), (32, 8, 3, 3), (32, 8, 4, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2), (32, 16, 4, 1),
-                (64, 4, 4, 3), (64, 4, 4, 2), (64, 8, 3, 2)]
+def _sweep_build():
+    try:
+        import sgc_b200
+        return bool(sgc_b200._lib.lib.sgc_build_flags() & 1)
+    except Exception:
+        return False
+
+
+# the product library carries four ring configurations of the fused curl (and one tile of its first generation); the
+# whole matrix of the tuning sweeps only exists in a `make EXTRA=-DSGC_SWEEP_BUILD` library
+RING_CONFIGS = [(32, 4, 6, 4), (32, 4, 4, 4), (32, 8, 4, 3), (64, 4, 4, 3)]
+V1_TILES = [(32, 8)]
+if _sweep_build():
+    RING_CONFIGS += [(32, 4, 3, 4), (32, 4, 5, 4), (32, 4, 7, 4), (32, 4, 8, 3), (32, 8, 3, 3), (32, 8, 4, 2), (32, 8, 6, 2), (32, 16, 3, 2),
+                     (32, 16, 4, 1), (64, 4, 4, 2), (64, 8, 3, 2)]
+    V1_TILES += [(32, 4), (32, 16), (64, 4), (64, 8)]
 FUSED_VARIANTS = [(tx, ty, 0 | (st << 4) | (mb << 8) | (xs << 12)) for (tx, ty, st, mb) in RING_CONFIGS for xs in (0, 1)]
-FUSED_VARIANTS += [(tx, ty, 1) for (tx, ty) in [(32, 4), (32, 8), (32, 16), (64, 4), (64, 8)]]
+FUSED_VARIANTS += [(tx, ty, 1) for (tx, ty) in V1_TILES]
 
 
 @pytest.mark.parametrize("cfg", FUSED_VARIANTS)
@@ -431,12 +445,12 @@ def test_fused_divg_grad_slab_split_equals_whole(S):
 # ------------------------------------------------------------------------------------------------
 # fused curl-of-curl (k_curlcurl3): one pass, H never written — bit-identical to two apply_curl!
 # ------------------------------------------------------------------------------------------------
-# (tile_x, tile_y, march, ring stages, kernel version): version 0 = automatic (the TMA-fed warp-specialised kernel
-# k_cc4 for ComplexF64 grids that hold a tile, else the third generation), 4 = k_cc4 as configured (stages = E ring |
-# H ring << 4), 2 = third generation (warp roles, cp.async), 1 = first generation
-CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 8, 3, 3, 2), (32, 7, 5, 4, 2), (32, 4, 2, 4, 2), (32, 7, 1, 3, 2), (32, 4, 7, 3, 2),
-                    (32, 8, 3, 3, 1), (32, 4, 2, 4, 1), (64, 4, 6, 3, 1),
-                    (32, 8, 3, 0x34, 4), (32, 8, 1, 0x45, 4), (32, 6, 5, 0x34, 4), (32, 10, 2, 0x34, 4), (32, 12, 7, 0x34, 4)]
+# (tile_x, tile_y, march, ring stages, kernel version): version 0 / 2 = third generation (warp roles, cp.async; the
+# default), 1 = first generation, 4 = the TMA-fed warp-specialised experiment k_cc4 where it applies (ComplexF64, no Bloch
+# wrap in x / y, no slab ghosts; tile_y 6 or 8), else the third generation
+CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 7, 3, 3, 2), (32, 7, 5, 4, 2), (32, 4, 2, 4, 2), (32, 7, 1, 3, 2), (32, 4, 7, 4, 2),
+                    (32, 8, 3, 3, 1), (32, 8, 2, 3, 1), (32, 8, 6, 3, 1),
+                    (0, 6, 3, 0, 4), (0, 8, 1, 0, 4), (0, 6, 0, 0, 4)]
 
 
 def _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, tilings, what):

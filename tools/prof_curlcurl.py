@@ -15,7 +15,7 @@ d1 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for _ in range(3)]
 d2 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for _ in range(3)]
 c1 = S.Operator.curl(S.SGC_C128, N, [True] * 3, d1, [False] * 3, [1.0] * 3)
 c2 = S.Operator.curl(S.SGC_C128, N, [False] * 3, d2, [False] * 3, [1.0] * 3)
-c2.set_tuning(tx, ty, march, (se << 4) | (int(sys.argv[5]) if len(sys.argv) > 5 else 0))
+c2.set_tuning(tx, ty, march, (se << 4) | (int(sys.argv[5]) if len(sys.argv) > 5 else 0))  # se may carry the H-ring stages in its high nibble
 for _ in range(4):
     c2.apply_after(c1, G, E, "=")
 torch.cuda.synchronize()
