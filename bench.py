@@ -767,9 +767,8 @@ def bench_assembly_partitioned(S, torch, dist, rank, world):
     rank r assembles its block of columns — the global rowval / nzval are the concatenation of the blocks' arrays
     and every rank does exactly 1/N of the single-GPU work.  No exchange; the time is the max over ranks, the rate
     the whole matrix's nnz over that time."""
-    res = _bench_assembly_part(S, torch, dist, rank, world, by_cols=False)
-    cols = _bench_assembly_part(S, torch, dist, rank, world, by_cols=True)
-    res["column_partition"] = cols
+    res = _bench_assembly_part(S, torch, dist, rank, world, by_cols=True)   # the scalable form first
+    res["row_partition"] = _bench_assembly_part(S, torch, dist, rank, world, by_cols=False)
     return res
 
 
@@ -826,7 +825,8 @@ def _bench_assembly_part(S, torch, dist, rank, world, by_cols):
         lib.sgc_asm_destroy(h)
         ms, total = float(tmax[0]), int(t[1])
         if by_cols:
-            return {"workload": f"the same matrix as {world} per-GPU blocks of COLUMNS (global rowval / nzval = concatenation)",
+            return {"workload": f"create_curl 512^3 Float64 all-Bloch partitioned into {world} per-GPU CSC blocks of COLUMNS, no exchange "
+                                f"(global rowval / nzval = concatenation of the blocks' arrays, matrix/differential/curl.jl:103)",
                     "nnz": total, "ms": ms, "nnz_per_s": total / (ms * 1e-3), "nnz_ok": total == 12 * M,
                     "includes": "per rank: closed-form nnz and offsets + single fill pass over its columns (max over ranks)"}
         return {"workload": f"create_curl 512^3 Float64 all-Bloch, row-partitioned into {world} per-GPU CSC blocks (no exchange)",
@@ -919,6 +919,38 @@ def bench_other_configs(S, torch, peak, c_dual, c_prim, E, E2, ms_two_curls):
             alg = nnz * 16 + (ncol + 1) * 8
             asm[name] = {"ms": r4(ms), "gnnz_per_s": r4(nnz / ms / 1e6), "frac": r4(alg / ms / 1e6 / peak)}
         res["assembly_others_384_f64"] = asm
+        # call latency of the reference-shaped one-shot entry point (handle cached inside the library) against a held
+        # handle, on a 64³ grid where the kernel itself takes ~10 µs (BASELINE configs[0] size)
+        import ctypes as C
+        import time as _t
+        from sgc_b200._lib import lib, check
+        from sgc_b200.device import ints, int64s, scalars2, scalar2, stream_handle, coef_vectors
+        n6 = (64, 64, 64)
+        d6 = [rng.uniform(0.5, 1.5, 64) + 1j * rng.uniform(-.2, .2, 64) for _ in range(3)]
+        F6 = S.DeviceArray(torch.view_as_complex(torch.rand(3 * 64 ** 3, 2, device="cuda", dtype=torch.float64)), n6 + (3,))
+        G6 = S.DeviceArray.zeros(n6 + (3,))
+        arr, keep, cc = coef_vectors(d6, n6)
+        e6 = list(np.exp(-2j * np.pi * np.array([0.1, 0.2, 0.3])))
+        args = (C.c_void_p(G6.ptr), C.c_void_p(F6.ptr), 0, S.SGC_C128, 3, int64s(n6), ints([1, 1, 1]), arr, cc, ints([1, 1, 1]), scalars2(e6),
+                ints([1, 2, 3]), 3, ints([1, 2, 3]), 3, ints([1, 2, 3]), scalar2(1.0), stream_handle())
+        lib.sgc_oneshot_cache_clear()
+        torch.cuda.synchronize()
+        t0 = _t.perf_counter(); check(lib.sgc_apply_curl(*args)); torch.cuda.synchronize(); first_us = (_t.perf_counter() - t0) * 1e6
+        reps = 300
+        t0 = _t.perf_counter()
+        for _ in range(reps):
+            check(lib.sgc_apply_curl(*args))
+        torch.cuda.synchronize()
+        cached_us = (_t.perf_counter() - t0) * 1e6 / reps
+        o6 = S.Operator.curl(S.SGC_C128, n6, [True] * 3, d6, [True] * 3, e6)
+        o6.apply(G6, F6, "=")
+        torch.cuda.synchronize()
+        t0 = _t.perf_counter()
+        for _ in range(reps):
+            o6.apply(G6, F6, "=")
+        torch.cuda.synchronize()
+        handle_us = (_t.perf_counter() - t0) * 1e6 / reps
+        res["call_latency_us_64cubed_curl"] = {"one_shot_first_call": r4(first_us), "one_shot_cached": r4(cached_us), "held_handle": r4(handle_us)}
     except Exception as ex:
         res["error"] = str(ex)[:200]
     return res

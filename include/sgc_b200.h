@@ -164,9 +164,12 @@ int sgc_op_destroy(sgc_op *op);
 int sgc_op_launches(const sgc_op *op, int opmode);
 
 /* ---------------------------------------------------------------------------------------- */
-/* Matrix-free operators: one-shot calls with the reference's argument lists (create a       */
-/* transient handle, apply, destroy).                                                        */
+/* Matrix-free operators: one-shot calls with the reference's argument lists.  The handle     */
+/* behind a call is cached (keyed by every parameter, coefficient vectors by content; 32      */
+/* entries, least recently used evicted), so a repeated call only queues its kernel and       */
+/* returns without synchronising.                                                             */
 /* ---------------------------------------------------------------------------------------- */
+int sgc_oneshot_cache_clear(void);
 int sgc_apply_partial(void *Gv, const void *Fu, int opmode, int dtype, int ndim, const int64_t *N,
                       int nw, int isfwd, const void *dwinv, int coef_complex, int isbloch,
                       const double *e, const double *alpha, void *stream);

@@ -43,6 +43,7 @@ vpp = C.POINTER(C.c_void_p)
 _PROTOS = {
     "sgc_abi_version": (C.c_int, []),
     "sgc_build_flags": (C.c_int, []),
+    "sgc_oneshot_cache_clear": (C.c_int, []),
     "sgc_last_error": (C.c_char_p, []),
     "sgc_device_count": (C.c_int, [intp]),
     "sgc_set_device": (C.c_int, [C.c_int]),

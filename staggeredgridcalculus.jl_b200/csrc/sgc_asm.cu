@@ -27,13 +27,13 @@ static void free_checked(void *p, const char *what) {
 
 extern "C" int sgc_asm_destroy(sgc_asm *a) {
     if (!a) return SGC_OK;
-    free_checked(a->arena, "asm arena");
+    if (a->arena) {  // stream-ordered: after the last kernel that reads the tables, without a device-wide synchronisation
+        if (cudaFreeAsync(a->arena, a->last_stream) != cudaSuccess) cudaGetLastError();
+    }
     free_checked(a->scan_tmp, "scan scratch");
     free_checked(a->d_colptr, "host-path colptr");
     free_checked(a->cta_total, "cta totals");
     free_checked(a->cta_offset, "cta offsets");
-    free_checked(a->count_tables, "count tables");
-    free_checked(a->prefix_tables, "prefix tables");
     delete a;
     return SGC_OK;
 }
@@ -109,15 +109,14 @@ static AsmBlockHost mean_block(const sgc_asm *a, int nv, int nu, int axis, int i
     return B;
 }
 
+// One stream-ordered allocation and one upload per handle: [V₀/Vₛ value tables | count tables | prefix tables].
+// (cudaMalloc / cudaFree each synchronise the device; against a sub-millisecond fill kernel they dominated create_*.)
 static int finish_asm(sgc_asm *a) {
     OpBuilder b;
     for (auto &B : a->blocks) {
         a->off0.push_back(b.push(B.V0, a->cx));
         a->offs.push_back(b.push(B.Vs, a->cx));
     }
-    size_t bytes = b.host.size() ? b.host.size() : 16;
-    CUDA_TRY(cudaMalloc(&a->arena, bytes));
-    if (b.host.size()) CUDA_TRY(cudaMemcpy(a->arena, b.host.data(), b.host.size(), cudaMemcpyHostToDevice));
     a->row_begin = 0;
     a->row_end = (int64_t)a->Kout * a->M;
     // separable count tables: A[nu][axis][i] = number of nonzero values the blocks of block column
@@ -145,8 +144,6 @@ static int finish_asm(sgc_asm *a) {
             }
         }
     }
-    CUDA_TRY(cudaMalloc((void **)&a->count_tables, sizeof(int) * tab.size()));
-    CUDA_TRY(cudaMemcpy(a->count_tables, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice));
     // exclusive prefix sums of the count tables (sets 0..2: one block column; set 3: all of them) for
     // the closed-form entry offsets of the fill kernel
     std::vector<int64_t> pre;
@@ -166,8 +163,17 @@ static int finish_asm(sgc_asm *a) {
         a->set_total[set] = a->N[1] * a->N[2] * S[0] + a->N[0] * a->N[2] * S[1] + a->N[0] * a->N[1] * S[2];
     }
     a->h_prefix = pre;
-    CUDA_TRY(cudaMalloc((void **)&a->prefix_tables, sizeof(int64_t) * pre.size()));
-    CUDA_TRY(cudaMemcpy(a->prefix_tables, pre.data(), sizeof(int64_t) * pre.size(), cudaMemcpyHostToDevice));
+    const size_t off_tab = (b.host.size() + 15) & ~size_t(15);
+    const size_t off_pre = (off_tab + sizeof(int) * tab.size() + 15) & ~size_t(15);
+    const size_t bytes = off_pre + sizeof(int64_t) * pre.size();
+    b.host.resize(bytes);
+    memcpy(b.host.data() + off_tab, tab.data(), sizeof(int) * tab.size());
+    memcpy(b.host.data() + off_pre, pre.data(), sizeof(int64_t) * pre.size());
+    CUDA_TRY(cudaMallocAsync(&a->arena, bytes, (cudaStream_t)0));
+    CUDA_TRY(cudaMemcpyAsync(a->arena, b.host.data(), bytes, cudaMemcpyHostToDevice, (cudaStream_t)0));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));  // (the staging vector dies with this call)
+    a->count_tables = (int *)((unsigned char *)a->arena + off_tab);
+    a->prefix_tables = (int64_t *)((unsigned char *)a->arena + off_pre);
     return SGC_OK;
 }
 
@@ -482,6 +488,14 @@ static int asm_count(sgc_asm *a, cudaStream_t st) {
         a->counted = true;
         return SGC_OK;
     }
+    if (a->row_begin == 0 && a->row_end == (int64_t)a->Kout * a->M && a->prefix_tables && !a->force_count_pass) {
+        // all rows kept: the count is separable and the fill kernel derives its offsets in closed form
+        // (AsmParams::prefix) — no count kernel, no scan, no read-back, no per-CTA arrays
+        a->ncta = ncta;
+        a->nnz = a->set_total[3];
+        a->counted = true;
+        return SGC_OK;
+    }
     if (ncta != a->ncta || !a->cta_total) {
         if (a->cta_total) cudaFree(a->cta_total);
         if (a->cta_offset) cudaFree(a->cta_offset);
@@ -542,6 +556,7 @@ extern "C" int sgc_asm_count(sgc_asm *a, int64_t *nnz, void *stream) {
 
 extern "C" int sgc_asm_fill_all(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval, void *stream) {
     REQUIRE(a && colptr, "NULL argument");
+    a->last_stream = (cudaStream_t)stream;
     REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
     int s = asm_count(a, (cudaStream_t)stream);
     if (s) return s;
@@ -556,6 +571,7 @@ extern "C" int sgc_asm_fill_all(sgc_asm *a, int64_t *colptr, int index_base, int
 
 extern "C" int sgc_asm_colptr(sgc_asm *a, int64_t *colptr, int index_base, int64_t *nnz, void *stream) {
     REQUIRE(a && colptr, "NULL argument");
+    a->last_stream = (cudaStream_t)stream;
     REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
     int s = asm_count(a, (cudaStream_t)stream);
     if (s) return s;
@@ -568,6 +584,7 @@ extern "C" int sgc_asm_fill(const sgc_asm *a, const int64_t *colptr, int index_b
     REQUIRE(a && colptr, "NULL argument");
     REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
     REQUIRE(a->counted, "call sgc_asm_colptr (or sgc_asm_count) before sgc_asm_fill");
+    a->last_stream = (cudaStream_t)stream;
     return asm_dispatch<ASM_FILL>(a, index_base, colptr, nullptr, rowval, nzval, (cudaStream_t)stream);
 }
 

@@ -186,6 +186,7 @@ int coo_sort_typed(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval,
 
 extern "C" int sgc_asm_coo_sort(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowval, void *nzval,
                                 int64_t nnz_capacity, int64_t *nnz, void *stream) {
+    if (a) a->last_stream = (cudaStream_t)stream;
     REQUIRE(a && colptr && ((rowval && nzval) || nnz_capacity == 0), "NULL argument");
     REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
     if (a->cx) return coo_sort_typed<cplx>(a, colptr, index_base, rowval, (cplx *)nzval, nnz_capacity, nnz, (cudaStream_t)stream);

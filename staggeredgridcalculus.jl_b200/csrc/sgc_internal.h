@@ -78,7 +78,8 @@ struct sgc_asm {
     bool cx = false;  // value type is ComplexF64
     std::vector<AsmBlockHost> blocks;
     int64_t row_begin = 0, row_end = 0;
-    void *arena = nullptr;
+    void *arena = nullptr;            // device: value tables, count tables, prefix tables (one allocation)
+    mutable cudaStream_t last_stream = nullptr;  // stream of the last fill (the arena is freed in its order)
     std::vector<size_t> off0, offs;
     void *scan_tmp = nullptr;
     size_t scan_tmp_bytes = 0;

@@ -7,6 +7,7 @@
 #include "sgc_internal.h"
 
 #include <algorithm>
+#include <mutex>
 
 #include "sgc_kernels.cuh"
 #include "sgc_fused.cuh"
@@ -757,48 +758,127 @@ extern "C" int sgc_op_launches(const sgc_op *op, int opmode) {
 }
 
 // ---- one-shot calls -------------------------------------------------------------------------------
-#define ONE_SHOT(create_call, G, F)                          \
-    sgc_op *op = nullptr;                                    \
-    int s = create_call;                                     \
-    if (s) return s;                                         \
-    s = sgc_op_apply(op, G, F, opmode, stream);              \
-    /* tables must outlive the queued kernels */             \
-    if (!s) { cudaError_t ce = cudaStreamSynchronize((cudaStream_t)stream); \
-              if (ce != cudaSuccess) s = fail(SGC_ERR_CUDA, "sync failed: %s", cudaGetErrorString(ce)); } \
-    sgc_op_destroy(op);                                      \
-    return s;
+// The reference's calls carry every parameter each time (apply_∂!(Gv, Fu, Val(OP), nw, isfwd, ∆w⁻¹, isbloch, e; α)).  A
+// transient handle per call would cost a table upload, two allocations and a stream synchronisation against a kernel
+// of a few hundred microseconds, so the handles live in a small cache keyed by EVERYTHING that defines the operator
+// (the coefficient vectors by content): a repeated call — a solver loop written against the reference's API — finds
+// its tables resident and only queues the kernel; the call returns without synchronising.
+namespace {
+struct OneShotKey {
+    std::string k;
+    void raw(const void *p, size_t n) { k.append((const char *)p, n); }
+    template <typename V> void val(V v) { raw(&v, sizeof v); }
+    void ints(const int *p, int n) { val(n); if (p) raw(p, sizeof(int) * (size_t)n); else val((char)0); }
+    void vec(const void *p, int64_t n, int cc) { val((char)(p ? 1 : 0)); if (p) raw(p, (size_t)n * (cc ? 16 : 8)); }
+    void pair(const double *p) { if (p) raw(p, 16); else val((char)0); }
+    void pairs(const double *p, int n) { if (p) raw(p, 16 * (size_t)n); else val((char)0); }
+};
+struct OneShotEntry { std::string key; sgc_op *op; uint64_t used; };
+std::mutex g_oneshot_mu;
+std::vector<OneShotEntry> g_oneshot;
+uint64_t g_oneshot_clock = 0;
+constexpr size_t ONESHOT_CAPACITY = 32;
+
+sgc_op *oneshot_find(const std::string &key) {
+    std::lock_guard<std::mutex> lock(g_oneshot_mu);
+    for (auto &e : g_oneshot)
+        if (e.key == key) { e.used = ++g_oneshot_clock; return e.op; }
+    return nullptr;
+}
+void oneshot_keep(std::string key, sgc_op *op) {
+    sgc_op *victim = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_oneshot_mu);
+        if (g_oneshot.size() >= ONESHOT_CAPACITY) {
+            size_t lru = 0;
+            for (size_t q = 1; q < g_oneshot.size(); ++q)
+                if (g_oneshot[q].used < g_oneshot[lru].used) lru = q;
+            victim = g_oneshot[lru].op;
+            g_oneshot.erase(g_oneshot.begin() + lru);
+        }
+        g_oneshot.push_back(OneShotEntry{std::move(key), op, ++g_oneshot_clock});
+    }
+    if (victim) sgc_op_destroy(victim);  // (cudaFree waits for the kernels that still read its tables)
+}
+void key_head(OneShotKey &k, int tag, int dtype, int ndim, const int64_t *N) {
+    int dev = -1;
+    cudaGetDevice(&dev);
+    k.val(tag); k.val(dev); k.val(dtype); k.val(ndim);
+    for (int d = 0; d < ndim && d < 3; ++d) k.val(N ? N[d] : (int64_t)0);
+}
+}  // namespace
+
+// drops every cached one-shot operator (tests; before a device reset)
+extern "C" int sgc_oneshot_cache_clear(void) {
+    std::vector<OneShotEntry> old;
+    {
+        std::lock_guard<std::mutex> lock(g_oneshot_mu);
+        old.swap(g_oneshot);
+    }
+    for (auto &e : old) sgc_op_destroy(e.op);
+    return SGC_OK;
+}
+
+#define ONE_SHOT(keyexpr, create_call, G, F)                 \
+    if (sgc_check_common(dtype, ndim, N)) return SGC_ERR_INVALID; \
+    OneShotKey key;                                          \
+    keyexpr;                                                 \
+    sgc_op *op = oneshot_find(key.k);                        \
+    if (!op) {                                               \
+        int s = create_call;                                 \
+        if (s) return s;                                     \
+        oneshot_keep(key.k, op);                             \
+    }                                                        \
+    return sgc_op_apply(op, G, F, opmode, stream);
 
 extern "C" int sgc_apply_partial(void *Gv, const void *Fu, int opmode, int dtype, int ndim, const int64_t *N,
                                  int nw, int isfwd, const void *dwinv, int coef_complex, int isbloch,
                                  const double *e, const double *alpha, void *stream) {
-    ONE_SHOT(sgc_op_create_partial(&op, dtype, ndim, N, nw, isfwd, dwinv, coef_complex, isbloch, e, alpha), Gv, Fu)
+    REQUIRE(nw >= 1 && nw <= ndim && ndim <= 3, "nw = %d out of range 1..%d", nw, ndim);
+    ONE_SHOT((key_head(key, 1, dtype, ndim, N), key.val(nw), key.val(isfwd), key.val(coef_complex), key.val(isbloch), key.pair(e), key.pair(alpha),
+              key.vec(dwinv, N[nw - 1], coef_complex)),
+             sgc_op_create_partial(&op, dtype, ndim, N, nw, isfwd, dwinv, coef_complex, isbloch, e, alpha), Gv, Fu)
 }
 extern "C" int sgc_apply_mhat(void *Gv, const void *Fu, int opmode, int dtype, int ndim, const int64_t *N,
                               int nw, int isfwd, const void *dw, const void *dwpinv, int coef_complex,
                               int isbloch, const double *e, const double *alpha, void *stream) {
-    ONE_SHOT(sgc_op_create_mhat(&op, dtype, ndim, N, nw, isfwd, dw, dwpinv, coef_complex, isbloch, e, alpha), Gv, Fu)
+    REQUIRE(nw >= 1 && nw <= ndim && ndim <= 3, "nw = %d out of range 1..%d", nw, ndim);
+    ONE_SHOT((key_head(key, 2, dtype, ndim, N), key.val(nw), key.val(isfwd), key.val(coef_complex), key.val(isbloch), key.pair(e), key.pair(alpha),
+              key.vec(dw, N[nw - 1], coef_complex), key.vec(dwpinv, N[nw - 1], coef_complex)),
+             sgc_op_create_mhat(&op, dtype, ndim, N, nw, isfwd, dw, dwpinv, coef_complex, isbloch, e, alpha), Gv, Fu)
 }
 extern "C" int sgc_apply_curl(void *G, const void *F, int opmode, int dtype, int ndim, const int64_t *N,
                               const int *isfwd, const void *const *dlinv, int coef_complex, const int *isbloch,
                               const double *e, const int *cmp_shp, int Kout, const int *cmp_out, int Kin,
                               const int *cmp_in, const double *alpha, void *stream) {
-    ONE_SHOT(sgc_op_create_curl(&op, dtype, ndim, N, isfwd, dlinv, coef_complex, isbloch, e, cmp_shp, Kout,
-                                cmp_out, Kin, cmp_in, alpha), G, F)
+    REQUIRE(isfwd && isbloch && cmp_shp && cmp_out && cmp_in && Kout >= 1 && Kout <= 3 && Kin >= 1 && Kin <= 3, "bad arguments");
+    ONE_SHOT((key_head(key, 3, dtype, ndim, N), key.ints(isfwd, ndim), key.ints(isbloch, ndim), key.ints(cmp_shp, ndim), key.ints(cmp_out, Kout),
+              key.ints(cmp_in, Kin), key.val(coef_complex), key.pairs(e, ndim), key.pair(alpha),
+              [&] { for (int d = 0; d < ndim; ++d) key.vec(dlinv ? dlinv[d] : nullptr, N[d], coef_complex); }()),
+             sgc_op_create_curl(&op, dtype, ndim, N, isfwd, dlinv, coef_complex, isbloch, e, cmp_shp, Kout, cmp_out, Kin, cmp_in, alpha), G, F)
 }
 extern "C" int sgc_apply_divg(void *g, const void *F, int opmode, int dtype, int ndim, const int64_t *N,
                               const int *isfwd, const void *const *dlinv, int coef_complex, const int *isbloch,
                               const double *e, const double *alpha, void *stream) {
-    ONE_SHOT(sgc_op_create_divg(&op, dtype, ndim, N, isfwd, dlinv, coef_complex, isbloch, e, alpha), g, F)
+    REQUIRE(isfwd && isbloch, "NULL argument");
+    ONE_SHOT((key_head(key, 4, dtype, ndim, N), key.ints(isfwd, ndim), key.ints(isbloch, ndim), key.val(coef_complex), key.pairs(e, ndim), key.pair(alpha),
+              [&] { for (int d = 0; d < ndim; ++d) key.vec(dlinv ? dlinv[d] : nullptr, N[d], coef_complex); }()),
+             sgc_op_create_divg(&op, dtype, ndim, N, isfwd, dlinv, coef_complex, isbloch, e, alpha), g, F)
 }
 extern "C" int sgc_apply_grad(void *G, const void *f, int opmode, int dtype, int ndim, const int64_t *N,
                               const int *isfwd, const void *const *dlinv, int coef_complex, const int *isbloch,
                               const double *e, const double *alpha, void *stream) {
-    ONE_SHOT(sgc_op_create_grad(&op, dtype, ndim, N, isfwd, dlinv, coef_complex, isbloch, e, alpha), G, f)
+    REQUIRE(isfwd && isbloch, "NULL argument");
+    ONE_SHOT((key_head(key, 5, dtype, ndim, N), key.ints(isfwd, ndim), key.ints(isbloch, ndim), key.val(coef_complex), key.pairs(e, ndim), key.pair(alpha),
+              [&] { for (int d = 0; d < ndim; ++d) key.vec(dlinv ? dlinv[d] : nullptr, N[d], coef_complex); }()),
+             sgc_op_create_grad(&op, dtype, ndim, N, isfwd, dlinv, coef_complex, isbloch, e, alpha), G, f)
 }
 extern "C" int sgc_apply_mean(void *G, const void *F, int opmode, int dtype, int ndim, const int64_t *N,
                               const int *isfwd, const void *const *dl, const void *const *dlpinv,
                               int coef_complex, const int *isbloch, const double *e, const double *alpha,
                               void *stream) {
-    ONE_SHOT(sgc_op_create_mean(&op, dtype, ndim, N, isfwd, dl, dlpinv, coef_complex, isbloch, e, alpha), G, F)
+    REQUIRE(isfwd && isbloch, "NULL argument");
+    ONE_SHOT((key_head(key, 6, dtype, ndim, N), key.ints(isfwd, ndim), key.ints(isbloch, ndim), key.val(coef_complex), key.pairs(e, ndim), key.pair(alpha),
+              [&] { for (int d = 0; d < ndim; ++d) { key.vec(dl ? dl[d] : nullptr, N[d], coef_complex); key.vec(dlpinv ? dlpinv[d] : nullptr, N[d], coef_complex); } }()),
+             sgc_op_create_mean(&op, dtype, ndim, N, isfwd, dl, dlpinv, coef_complex, isbloch, e, alpha), G, F)
 }
-
