@@ -319,7 +319,14 @@ class Leg:
     def time(self, steps, warmup, use_graph, local_rank):
         torch, dist, S = self.torch, self.dist, self.S
         self.resync()
+        t_w = time.perf_counter()
         for _ in range(warmup):
+            self.step()
+        self.barrier()
+        # W steps are a floor, not a duration: after the oracle comparison (seconds of CPU work, idle GPUs and NVLink
+        # links) a few milliseconds of stepping do not bring clocks and links back up — keep stepping for ~0.2 s
+        per_step = max((time.perf_counter() - t_w) / max(warmup, 1), 1e-5)
+        for _ in range(min(2000, int(0.2 / per_step))):
             self.step()
         self.barrier()
         graph, launches_per_step, run_step = None, None, self.step
@@ -346,7 +353,7 @@ class Leg:
                 graph = None
             if graph is not None:
                 run_step = graph.replay
-                for _ in range(2):
+                for _ in range(max(2, warmup)):
                     run_step()
         self.barrier()
         if self.arena is not None:
