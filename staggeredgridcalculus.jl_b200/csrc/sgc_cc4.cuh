@@ -315,4 +315,199 @@ __global__ void __launch_bounds__(32 * (2 * TY + 3), 1) k_cc4(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// k_cc5 — fifth generation: the thread mapping of the third (every warp owns one H row AND one output row, two CTAs per
+// SM, one __syncthreads per plane), fed by TMA like the fourth, with the lean loops of the fourth.  What the profiles
+// said: v3 spends 365 of its 497 thread-instructions per cell on anything but FP64 — per-thread address arithmetic and
+// issue logic of the cp.async copies, branches around the boundary rules — and its copies cost 15 shared-memory
+// wavefronts per request; v4 removed both but gave up the two independent CTAs per SM that keep an SM busy while one
+// tile sits in its barrier.  Here one elected thread issues three box copies per plane (no address arithmetic anywhere
+// else), completion is an mbarrier try-wait right before first use, the boundary rules are out of line
+// (curl_point4), and the per-plane __syncthreads only orders the H ring.
+// Same applicability as k_cc4: ComplexF64, symmetric x / y boundaries (out-of-range box cells are zero-filled, which is
+// what those rules discard), no slab ghost planes.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr size_t cc5_smem_bytes(int TY, int SE) {
+    return (size_t)SE * 3 * cc4_ecb(TY) + (size_t)3 * 3 * 33 * (TY + 1) * 16 + 8 * SE + 128;
+}
+
+template <typename C, bool ADD, int TY, int SE, bool FZ1, bool FZ2>
+__global__ void __launch_bounds__(32 * (TY + 1), 2) k_cc5(const __grid_constant__ CurlCurl4Params<C> P) {
+    using T = cplx;
+    static_assert(SE >= 3, "need at least 3 stages");
+    const CurlCurlParams<T, C> &p = P.q;
+    constexpr int TX = 32;
+    constexpr int HX = TX + 1, HY = TY + 1, EX = TX + 2, EY = TY + 2;
+    constexpr int ES = 16;
+    constexpr int ECOMP = EX * EY;
+    constexpr int ECB = cc4_ecb(TY), HCB = HX * HY * ES;
+    constexpr int ESTAGE = 3 * ECB, HSTAGE = 3 * HCB;
+    static_assert(HY <= 32, "the extra column is handled by one warp");
+    extern __shared__ __align__(128) unsigned char sgc_smem_raw[];
+    const unsigned sE = ((unsigned)__cvta_generic_to_shared(sgc_smem_raw) + 127u) & ~127u;
+    const unsigned sH = sE + SE * ESTAGE;
+    const unsigned bar_efull = sH + 3 * HSTAGE;
+
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int Nx = p.Nx, Ny = p.Ny, Nz = p.Nz;
+    const int64_t sy = Nx, sz = (int64_t)Nx * Ny;
+    const bool fx1 = p.fwd1[0], fy1 = p.fwd1[1], fx2 = p.fwd2[0], fy2 = p.fwd2[1];
+    const int s1x = fx1 ? 1 : -1, s1y = fy1 ? 1 : -1, s2x = fx2 ? 1 : -1, s2y = fy2 ? 1 : -1;
+    constexpr int s1z = FZ1 ? 1 : -1, s2z = FZ2 ? 1 : -1;
+    const int i0 = blockIdx.x * TX, j0 = blockIdx.y * TY;
+    const int hx0 = i0 + min(0, s2x), hy0 = j0 + min(0, s2y);
+    const int ex0 = hx0 + min(0, s1x), ey0 = hy0 + min(0, s1y);
+    const T Z = zero_of(T{});
+    const int ox1 = s1x < 0 ? 1 : 0, oy1 = s1y < 0 ? 1 : 0;
+
+    const int k0 = p.k_begin + blockIdx.z * p.march;
+    const int k1 = min(k0 + p.march, p.k_end);
+    if (k0 >= k1) return;
+    const int n = k1 - k0;
+    const int hb = k0 + min(0, s2z);
+    const int eb = hb + min(0, s1z);
+    const int nslots = n + 2;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < SE; ++s) mbar_init(bar_efull + 8 * s, 1u);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---- producer duty of thread 0: E slot j → ring stage j mod SE ------------------------------------------------
+    int issue_slot = 0, issue_stage = 0;
+    auto issue = [&]() {
+        if (issue_slot < nslots) {
+            const int kp = wrap_index(eb + issue_slot, Nz);
+            const unsigned st = sE + issue_stage * ESTAGE, bar = bar_efull + 8 * issue_stage;
+            mbar_arrive_expect_tx(bar, 3 * ECOMP * ES);
+            tma_load_3d(st, &P.tm[0], bar, 2 * ex0, ey0, kp);
+            tma_load_3d(st + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp);
+            tma_load_3d(st + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp);
+        }
+        ++issue_slot;
+        issue_stage = (issue_stage + 1 == SE) ? 0 : issue_stage + 1;
+    };
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < SE; ++q) issue();
+    }
+
+    // ---- role A: H position (row w, column lane) ---------------------------------------------------------------------
+    const PosConst<C> ca = pos_const<C>(p.fwd1, p.bc1_lo, p.bc1_hi, p.c1, wrap_index(hx0 + lane, Nx), wrap_index(hy0 + w, Ny), Nx, Ny);
+    const unsigned a_q = (unsigned)(((w + oy1) * EX + (lane + ox1)) * ES);
+    const unsigned a_out = sH + (unsigned)((w * HX + lane) * ES);
+    const int e_dxb = s1x * ES, e_dyb = s1y * EX * ES;
+    // ---- second role: D (warps < TY) or B′ (warp TY, lanes < HY) -----------------------------------------------------
+    const bool roleD = (w < TY);
+    const bool roleB2 = (w == TY) && (lane < HY);
+    const int i = i0 + lane, j = j0 + w;
+    const bool valid = roleD && (i < Nx) && (j < Ny);
+    PosConst<C> cb;
+    unsigned b_q, b_out = 0;
+    if (roleD) {
+        b_q = (unsigned)(((w + (s2y < 0 ? 1 : 0)) * HX + (lane + (s2x < 0 ? 1 : 0))) * ES);
+        cb = pos_const<C>(p.fwd2, p.bc2_lo, p.bc2_hi, p.c2, valid ? i : 0, valid ? j : 0, Nx, Ny);
+    } else {
+        const int py = roleB2 ? lane : 0;
+        b_q = (unsigned)(((py + oy1) * EX + (TX + ox1)) * ES);
+        b_out = sH + (unsigned)((py * HX + TX) * ES);
+        cb = pos_const<C>(p.fwd1, p.bc1_lo, p.bc1_hi, p.c1, wrap_index(hx0 + TX, Nx), wrap_index(hy0 + py, Ny), Nx, Ny);
+    }
+    const int h_dxb = s2x * ES, h_dyb = s2y * HX * ES;
+
+    RingPos e_lo{0, 0};
+    mbar_wait(bar_efull, 0);  // E slot 0
+    T axlo = lds_at<0>(sE + a_q, T{}), aylo = lds_at<ECB>(sE + a_q, T{});
+    T bxlo = Z, bylo = Z;
+    if (!roleD) { bxlo = lds_at<0>(sE + b_q, T{}); bylo = lds_at<ECB>(sE + b_q, T{}); }
+    unsigned h_cur = 0;
+    int64_t off_out = (int64_t)k0 * sz + (int64_t)j * sy + i;
+
+    auto h_point = [&](unsigned q, const PosConst<C> &c, T &xlo_c, T &ylo_c, unsigned out, int zflags, C cz, unsigned e_lo_a, unsigned e_hi_a) {
+        const unsigned ahi = e_hi_a + q;
+        const unsigned ac = (FZ1 ? e_lo_a : e_hi_a) + q;
+        const T xhi = lds_at<0>(ahi, T{}), yhi = lds_at<ECB>(ahi, T{});
+        const T zc = lds_at<2 * ECB>(ac, T{});
+        const T x_yn = lds_at<0>(ac + e_dyb, T{}), z_yn = lds_at<2 * ECB>(ac + e_dyb, T{});
+        const T y_xn = lds_at<ECB>(ac + e_dxb, T{}), z_xn = lds_at<2 * ECB>(ac + e_dxb, T{});
+        T d0, d1, d2, d3, d4, d5;
+        curl_point4<T, C, FZ1>(c.flags | zflags, c.cxs, c.cys, fx1, fy1, cz, p.e1, p.e1_real, xlo_c, xhi, ylo_c, yhi, zc, x_yn, z_yn, y_xn,
+                               z_xn, d0, d1, d2, d3, d4, d5);
+        sts_at<0>(out + h_cur, add(add(Z, neg(d1)), d3));  // Gv .= 0 ; += (−∂zFy) ; += ∂yFz   (curl.jl:66-91)
+        sts_at<HCB>(out + h_cur, add(d0, neg(d5)));
+        sts_at<2 * HCB>(out + h_cur, add(neg(d2), d4));
+        xlo_c = xhi;
+        ylo_c = yhi;
+    };
+
+    int hk = hb;
+    for (int m = 0; m <= n + 1; ++m, ++hk) {
+        if (m >= 1 && threadIdx.x == 0) issue();  // E slot m − 1 + SE → the stage slot m − 1 used (free since the last barrier)
+        if (m <= n) {
+            int zflags = 0;
+            C cz;
+            if (hk > 0 && hk < Nz - 1) {
+                cz = p.c1[2][hk];
+            } else {
+                const int kk = wrap_index(hk, Nz);
+                cz = p.c1[2][kk];
+                if (FZ1) {
+                    if (kk == Nz - 1) zflags = ((p.bc1_hi[2] == BC_BLOCH) ? 1 : (p.bc1_hi[2] == BC_SYM ? 2 : 0)) << 8;
+                    if (kk == 0 && p.bc1_lo[2] == BC_SYM) zflags |= 1024;
+                } else if (kk == 0) {
+                    zflags = ((p.bc1_lo[2] == BC_BLOCH) ? 1 : (p.bc1_lo[2] == BC_SYM ? 2 : 0)) << 8;
+                }
+            }
+            RingPos e_hi = e_lo;
+            e_hi.advance<SE>();
+            mbar_wait(bar_efull + 8 * e_hi.stage, e_hi.phase);  // E slot m + 1 has landed
+            const unsigned e_lo_a = sE + e_lo.stage * ESTAGE, e_hi_a = sE + e_hi.stage * ESTAGE;
+            h_point(a_q, ca, axlo, aylo, a_out, zflags, cz, e_lo_a, e_hi_a);
+            if (roleB2) h_point(b_q, cb, bxlo, bylo, b_out, zflags, cz, e_lo_a, e_hi_a);
+            e_lo = e_hi;
+        }
+        if (roleD && m >= 2) {
+            const int k = k0 + m - 2;
+            T g0 = Z, g1 = Z, g2 = Z;
+            if (ADD && valid) { g0 = ldg_plain(p.G[0] + off_out); g1 = ldg_plain(p.G[1] + off_out); g2 = ldg_plain(p.G[2] + off_out); }
+            const unsigned st_hi = (h_cur == 0) ? 2u * HSTAGE : h_cur - HSTAGE;   // slot m − 1
+            const unsigned st_lo = (st_hi == 0) ? 2u * HSTAGE : st_hi - HSTAGE;  // slot m − 2
+            const unsigned ahi = sH + st_hi + b_q, alo = sH + st_lo + b_q;
+            const unsigned ac = FZ2 ? alo : ahi;
+            if (m == 2) { bxlo = lds_at<0>(alo, T{}); bylo = lds_at<HCB>(alo, T{}); }
+            const T xhi = lds_at<0>(ahi, T{}), yhi = lds_at<HCB>(ahi, T{});
+            const T zc = lds_at<2 * HCB>(ac, T{});
+            const T x_yn = lds_at<0>(ac + h_dyb, T{}), z_yn = lds_at<2 * HCB>(ac + h_dyb, T{});
+            const T y_xn = lds_at<HCB>(ac + h_dxb, T{}), z_xn = lds_at<2 * HCB>(ac + h_dxb, T{});
+            const C cz = p.c2[2][k];
+            int zflags = 0;
+            if (k == 0 || k == Nz - 1) {
+                if (FZ2) {
+                    if (k == Nz - 1) zflags = ((p.bc2_hi[2] == BC_BLOCH) ? 1 : (p.bc2_hi[2] == BC_SYM ? 2 : 0)) << 8;
+                    if (k == 0 && p.bc2_lo[2] == BC_SYM) zflags |= 1024;
+                } else if (k == 0) {
+                    zflags = ((p.bc2_lo[2] == BC_BLOCH) ? 1 : (p.bc2_lo[2] == BC_SYM ? 2 : 0)) << 8;
+                }
+            }
+            T d0, d1, d2, d3, d4, d5;
+            curl_point4<T, C, FZ2>(cb.flags | zflags, cb.cxs, cb.cys, fx2, fy2, cz, p.e2, p.e2_real, bxlo, xhi, bylo, yhi, zc, x_yn, z_yn,
+                                   y_xn, z_xn, d0, d1, d2, d3, d4, d5);
+            T gx, gy, gz;
+            if (ADD) { gx = add(add(g0, neg(d1)), d3); gy = add(add(g1, d0), neg(d5)); gz = add(add(g2, neg(d2)), d4); }
+            else     { gx = add(add(Z, neg(d1)), d3);  gy = add(d0, neg(d5));          gz = add(neg(d2), d4); }
+            if (valid) {
+                stg_stream(p.G[0] + off_out, gx);
+                stg_stream(p.G[1] + off_out, gy);
+                stg_stream(p.G[2] + off_out, gz);
+            }
+            bxlo = xhi;
+            bylo = yhi;
+            off_out += sz;
+        }
+        if (m <= n) h_cur = (h_cur == 2u * HSTAGE) ? 0u : h_cur + HSTAGE;
+        __syncthreads();  // H plane m is complete; E slot m is free
+    }
+}
+
 }  // namespace sgc

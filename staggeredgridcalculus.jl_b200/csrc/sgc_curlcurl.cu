@@ -71,6 +71,32 @@ int launch_cc4_tiles(const CurlCurl4Params<C> &P, int ty, int se, int sh, dim3 g
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (TMA): tile 32x%d with %d/%d stages is not built", ty, se, sh);
 }
 
+template <typename C, bool ADD, int TY, int SE, bool FZ1, bool FZ2>
+int launch_cc5_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = cc5_smem_bytes(TY, SE);
+    auto kern = k_cc5<C, ADD, TY, SE, FZ1, FZ2>;
+    static std::atomic<uint64_t> attr_devices{0};
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
+    kern<<<grid, dim3(32 * (TY + 1), 1, 1), smem, st>>>(P);
+    return SGC_OK;
+}
+template <typename C, bool ADD, int TY, int SE>
+int launch_cc5_dirs(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
+    if (P.q.fwd1[2]) return P.q.fwd2[2] ? launch_cc5_one<C, ADD, TY, SE, true, true>(P, grid, st)
+                                        : launch_cc5_one<C, ADD, TY, SE, true, false>(P, grid, st);
+    return P.q.fwd2[2] ? launch_cc5_one<C, ADD, TY, SE, false, true>(P, grid, st)
+                       : launch_cc5_one<C, ADD, TY, SE, false, false>(P, grid, st);
+}
+template <typename C, bool ADD>
+int launch_cc5_tiles(const CurlCurl4Params<C> &P, int ty, int se, dim3 grid, cudaStream_t st) {
+#define CC5_CASE(TY, SE) if (ty == TY && se == SE) return launch_cc5_dirs<C, ADD, TY, SE>(P, grid, st);
+    CC5_CASE(7, 3)
+    CC5_CASE(7, 4)
+    CC5_CASE(5, 4)
+#undef CC5_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v5): tile 32x%d with %d stages is not built", ty, se);
+}
+
 // z-march that fills whole waves of one-CTA-per-SM: among the chunk counts with a march of at least 16 planes, the
 // one whose last wave is fullest (ties: the longer march, i.e. fewer halo planes)
 int cc4_march(int64_t tiles, int64_t nk) {
@@ -202,6 +228,22 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
         int ty4 = (c2->tile_y == 8) ? 8 : 6;
         const bool wraps_xy = a1.bloch[0] || a1.bloch[1] || a2.bloch[0] || a2.bloch[1];
         const bool ghosts = (ghost_lo && ghost_lo[0]) || (ghost_hi && ghost_hi[0]) || c1->lo_iface || c1->hi_iface;
+        if (version == 5 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= 9) {
+            const int ty5 = (c2->tile_y == 5) ? 5 : 7;
+            const int se5 = (((c2->variant >> 4) & 0xF) == 3 && ty5 == 7) ? 3 : 4;
+            CurlCurl4Params<C> P{};
+            P.q = p;
+            int s5 = SGC_OK;
+            for (int d = 0; d < 3 && !s5; ++d) s5 = encode_component(&P.tm[d], p.F[d], p.Nx, p.Ny, p.Nz, 34, ty5 + 2);
+            if (!s5) {
+                P.q.march = c2->march > 0 ? c2->march : (nk >= 256 ? 64 : 32);
+                dim3 g5((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty5 - 1) / ty5), (unsigned)((nk + P.q.march - 1) / P.q.march));
+                if (g5.y > 65535 || g5.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
+                s5 = add_mode ? launch_cc5_tiles<C, true>(P, ty5, se5, g5, st) : launch_cc5_tiles<C, false>(P, ty5, se5, g5, st);
+                if (s5) return s5;
+                return sgc_check_launch("k_cc5");
+            }
+        }
         if (version == 4 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= ty4 + 2) {
             CurlCurl4Params<C> P{};
             P.q = p;
@@ -220,7 +262,7 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
         }
     }
     int s;
-    if (version == 4) {  // k_cc4 asked for but not applicable (Float64 field, tiny grid): third generation with its own defaults
+    if (version == 4 || version == 5) {  // k_cc4 / k_cc5 asked for but not applicable (Float64 field, tiny grid): third generation with its own defaults
         const int ty3 = 7, se3 = sizeof(T) == 8 ? 4 : 3;
         p.march = nk >= 256 ? 64 : 32;
         dim3 g3((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty3 - 1) / ty3), (unsigned)((nk + p.march - 1) / p.march));
