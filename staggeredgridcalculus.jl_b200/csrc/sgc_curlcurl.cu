@@ -8,6 +8,7 @@
 
 #include "sgc_curlcurl.cuh"
 #include "sgc_cc4.cuh"
+#include "sgc_cc6.cuh"
 
 using namespace sgc;
 
@@ -95,6 +96,30 @@ int launch_cc5_tiles(const CurlCurl4Params<C> &P, int ty, int se, dim3 grid, cud
     CC5_CASE(5, 4)
 #undef CC5_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v5): tile 32x%d with %d stages is not built", ty, se);
+}
+
+// ---- sixth generation (sgc_cc6.cuh): two planes per barrier interval; C₁ forward / C₂ backward in z only ----------------
+template <typename C, bool ADD, int TY, int NP, int MINB>
+int launch_cc6_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = cc6_smem_bytes(TY, NP);
+    auto kern = k_cc6<C, ADD, TY, NP, MINB>;
+    static std::atomic<uint64_t> attr_devices{0};
+    CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
+    kern<<<grid, dim3(32 * (TY + 1), 1, 1), smem, st>>>(P);
+    return SGC_OK;
+}
+template <typename C, bool ADD>
+int launch_cc6_tiles(const CurlCurl4Params<C> &P, int ty, int np, dim3 grid, cudaStream_t st) {
+#define CC6_CASE(TY, NP, MINB) if (ty == TY && np == NP) return launch_cc6_one<C, ADD, TY, NP, MINB>(P, grid, st);
+    CC6_CASE(5, 3, 2)
+#ifdef SGC_SWEEP_BUILD
+    CC6_CASE(4, 4, 2)
+    CC6_CASE(4, 3, 2)
+    CC6_CASE(11, 3, 1)
+    CC6_CASE(9, 4, 1)
+#endif
+#undef CC6_CASE
+    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v6): tile 32x%d with %d pair stages is not built", ty, np);
 }
 
 // z-march that fills whole waves of one-CTA-per-SM: among the chunk counts with a march of at least 16 planes, the
@@ -228,6 +253,24 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
         int ty4 = (c2->tile_y == 8) ? 8 : 6;
         const bool wraps_xy = a1.bloch[0] || a1.bloch[1] || a2.bloch[0] || a2.bloch[1];
         const bool ghosts = (ghost_lo && ghost_lo[0]) || (ghost_hi && ghost_hi[0]) || c1->lo_iface || c1->hi_iface;
+        if (version == 6 && !wraps_xy && !ghosts && !a1.bloch[2] && !a2.bloch[2] && a1.fwd[2] && !a2.fwd[2] && p.Nx >= 34) {
+            const int ty6 = c2->tile_y ? c2->tile_y : 5;
+            const int np6 = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 3;
+            if (p.Ny >= ty6 + 2) {
+                CurlCurl4Params<C> P{};
+                P.q = p;
+                int s6 = SGC_OK;
+                for (int d = 0; d < 3 && !s6; ++d) s6 = encode_component(&P.tm[d], p.F[d], p.Nx, p.Ny, p.Nz, 34, ty6 + 2);
+                if (!s6) {
+                    P.q.march = std::min<int>(c2->march > 0 ? c2->march : 32, CC6_MAXMARCH);
+                    dim3 g6((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty6 - 1) / ty6), (unsigned)((nk + P.q.march - 1) / P.q.march));
+                    if (g6.y > 65535 || g6.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
+                    s6 = add_mode ? launch_cc6_tiles<C, true>(P, ty6, np6, g6, st) : launch_cc6_tiles<C, false>(P, ty6, np6, g6, st);
+                    if (s6) return s6;
+                    return sgc_check_launch("k_cc6");
+                }
+            }
+        }
         if (version == 5 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= 9) {
             const int ty5 = (c2->tile_y == 5) ? 5 : 7;
             const int se5 = (((c2->variant >> 4) & 0xF) == 3 && ty5 == 7) ? 3 : 4;
@@ -262,7 +305,7 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
         }
     }
     int s;
-    if (version == 4 || version == 5) {  // k_cc4 / k_cc5 asked for but not applicable (Float64 field, tiny grid): third generation with its own defaults
+    if (version == 4 || version == 5 || version == 6) {  // k_cc4 / k_cc5 / k_cc6 asked for but not applicable (Float64 field, tiny grid): third generation with its own defaults
         const int ty3 = 7, se3 = sizeof(T) == 8 ? 4 : 3;
         p.march = nk >= 256 ? 64 : 32;
         dim3 g3((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty3 - 1) / ty3), (unsigned)((nk + p.march - 1) / p.march));

@@ -447,10 +447,12 @@ def test_fused_divg_grad_slab_split_equals_whole(S):
 # ------------------------------------------------------------------------------------------------
 # (tile_x, tile_y, march, ring stages, kernel version): version 0 / 2 = third generation (warp roles, cp.async; the
 # default), 1 = first generation, 4 = the TMA-fed warp-specialised experiment k_cc4 where it applies (ComplexF64, no Bloch
-# wrap in x / y, no slab ghosts; tile_y 6 or 8), else the third generation
+# wrap in x / y, no slab ghosts; tile_y 6 or 8), else the third generation; 5 = k_cc5; 6 = k_cc6 (two planes per barrier interval;
+# C1 forward / C2 backward in z, ring stages = E pair stages), else the third generation
 CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 7, 3, 3, 2), (32, 7, 5, 4, 2), (32, 4, 2, 4, 2), (32, 7, 1, 3, 2), (32, 4, 7, 4, 2),
                     (32, 8, 3, 3, 1), (32, 8, 2, 3, 1), (32, 8, 6, 3, 1),
-                    (0, 6, 3, 0, 4), (0, 8, 1, 0, 4), (0, 6, 0, 0, 4), (0, 7, 3, 4, 5), (0, 7, 1, 3, 5), (0, 5, 2, 4, 5), (0, 7, 0, 0, 5)]
+                    (0, 6, 3, 0, 4), (0, 8, 1, 0, 4), (0, 6, 0, 0, 4), (0, 7, 3, 4, 5), (0, 7, 1, 3, 5), (0, 5, 2, 4, 5), (0, 7, 0, 0, 5),
+                    (0, 5, 0, 3, 6), (0, 5, 3, 3, 6), (0, 5, 8, 3, 6), (0, 5, 5, 3, 6)]
 
 
 def _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, tilings, what):
@@ -499,7 +501,7 @@ def test_fused_curlcurl_equals_two_curls(S, N, cplx_field, cplx_coef):
         for isbloch in ([True] * 3, [False] * 3, [True, False, True], [False, True, False]):
             if not all(isbloch[d] or N[d] >= 2 or not (isfwd1[d] or isfwd2[d]) for d in range(3)):
                 continue  # forward + symmetric on an axis of length 1 is rejected (reads Fu[2])
-            _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, CURLCURL_TILINGS[:3] + CURLCURL_TILINGS[6:7] + CURLCURL_TILINGS[9:10] + CURLCURL_TILINGS[12:13],
+            _curlcurl_case(S, rng, N, cplx_field, cplx_coef, isfwd1, isfwd2, isbloch, CURLCURL_TILINGS[:3] + CURLCURL_TILINGS[6:7] + CURLCURL_TILINGS[9:10] + CURLCURL_TILINGS[12:13] + CURLCURL_TILINGS[16:18],
                            f"curlcurl N={N} fwd1={isfwd1} fwd2={isfwd2} bloch={isbloch}")
 
 
