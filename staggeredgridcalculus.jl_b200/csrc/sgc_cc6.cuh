@@ -34,8 +34,15 @@ namespace sgc {
 
 constexpr int CC6_MAXMARCH = 64;
 constexpr int CC6_CZ = CC6_MAXMARCH + 4;  // entries of one staged coefficient table
+constexpr int cc6_epair(int TY) { return (6 * 34 * (TY + 2) * 16 + 127) / 128 * 128; }  // one pair of E planes, three components, whole lines
 constexpr size_t cc6_smem_bytes(int TY, int NP) {
-    return (size_t)NP * 2 * 3 * cc4_ecb(TY) + (size_t)4 * 3 * 33 * (TY + 1) * 16 + (size_t)2 * CC6_CZ * 16 + 8 * NP + 128;
+    return (size_t)NP * cc6_epair(TY) + (size_t)4 * 3 * 33 * (TY + 1) * 16 + (size_t)2 * CC6_CZ * 16 + 8 * NP + 128;
+}
+SGC_D void tma_load_4d(unsigned dst, const CUtensorMap *tm, unsigned bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 
 // The six ∂ terms at a point that a SYMMETRIC boundary rule touches (the rules of curl_point, sgc_curlcurl.cuh, without
@@ -68,7 +75,7 @@ SGC_D void curl_point_sym(int flags, C cxs, C cys, bool fx, bool fy, C cz, T xlo
     if (!fx && xedge) { d4 = Z; d5 = Z; }
 }
 
-template <typename C, bool ADD, int TY, int NP, int MINB>
+template <typename C, bool ADD, int TY, int NP, int MINB, bool SP>
 __global__ void __launch_bounds__(32 * (TY + 1), MINB) k_cc6(const __grid_constant__ CurlCurl4Params<C> P) {
     using T = cplx;
     static_assert(NP >= 3, "the E ring needs at least 3 pairs");
@@ -77,8 +84,10 @@ __global__ void __launch_bounds__(32 * (TY + 1), MINB) k_cc6(const __grid_consta
     constexpr int HX = TX + 1, HY = TY + 1, EX = TX + 2, EY = TY + 2;
     constexpr int ES = 16;
     constexpr int ECOMP = EX * EY;
-    constexpr int ECB = cc4_ecb(TY), HCB = HX * HY * ES;
-    constexpr int EPLANE = 3 * ECB, EPAIR = 2 * EPLANE, HSTAGE = 3 * HCB;
+    // one TMA box = (34 columns, TY+2 rows, 2 planes, 3 components) of the field array seen as a 4-D tensor: in shared
+    // memory component c of plane q of a pair sits at (2c + q)·EPLANE
+    constexpr int EPLANE = ECOMP * ES, ECB = 2 * EPLANE, EPAIR = cc6_epair(TY);
+    constexpr int HCB = HX * HY * ES, HSTAGE = 3 * HCB;
     constexpr int CS = (int)sizeof(C);
     static_assert(HY <= 32, "the extra column is handled by one warp");
     extern __shared__ __align__(128) unsigned char sgc_smem_raw[];
@@ -119,18 +128,15 @@ __global__ void __launch_bounds__(32 * (TY + 1), MINB) k_cc6(const __grid_consta
     __syncthreads();
 
     // ---- producer duty of thread 0: pair P_u → ring stage u mod NP ---------------------------------------------------
+    // ONE 4-D box copy per pair.  (Six 3-D copies from this thread put ≈ 150 instructions on warp 0's path to every
+    // barrier; spreading those six over the warps measured 6 % slower, and an additional L2 prefetch of the pair after
+    // next, cp.async.bulk.prefetch.tensor, changed nothing: profiles/r2_sweep_cc6_*.jsonl.)
     int issue_u = 0, issue_stage = 0;
     auto issue = [&]() {
-        if (issue_u <= Th) {
-            const int kp0 = wrap_index(hb + 2 * issue_u, Nz), kp1 = wrap_index(hb + 2 * issue_u + 1, Nz);
+        if (issue_u <= Th) {  // planes hb+2u, hb+2u+1: a plane outside the grid is zero-filled (and discarded by the symmetric rules)
             const unsigned st = sE + issue_stage * EPAIR, bar = bar_efull + 8 * issue_stage;
             mbar_arrive_expect_tx(bar, 6 * ECOMP * ES);
-            tma_load_3d(st, &P.tm[0], bar, 2 * ex0, ey0, kp0);
-            tma_load_3d(st + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp0);
-            tma_load_3d(st + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp0);
-            tma_load_3d(st + EPLANE, &P.tm[0], bar, 2 * ex0, ey0, kp1);
-            tma_load_3d(st + EPLANE + ECB, &P.tm[1], bar, 2 * ex0, ey0, kp1);
-            tma_load_3d(st + EPLANE + 2 * ECB, &P.tm[2], bar, 2 * ex0, ey0, kp1);
+            tma_load_4d(st, &P.tm[0], bar, 2 * ex0, ey0, hb + 2 * issue_u, 0);
         }
         ++issue_u;
         issue_stage = (issue_stage + 1 == NP) ? 0 : issue_stage + 1;
@@ -216,8 +222,86 @@ __global__ void __launch_bounds__(32 * (TY + 1), MINB) k_cc6(const __grid_consta
     unsigned h_wr = 0;                 // byte offset of the H pair written in iteration t (the other pair is being read)
     int64_t off_out = (int64_t)k0 * sz + (int64_t)j * sy + i;
 
+    // no H position (hence no output cell) of this tile lies on an x / y boundary, and the tile is whole
+    const bool tile_plain = (hx0 >= 1) && (hx0 + HX - 1 <= Nx - 2) && (hy0 >= 1) && (hy0 + HY - 1 <= Ny - 2);
+
     for (int t = 0; t <= Th + 1; ++t) {
         if (t >= 2 && threadIdx.x == 0) issue();  // P_{t−2+NP} → the stage P_{t−2} used (free since the last barrier)
+        // ---- steady state of a boundary-free tile (SP): both phases in ONE straight-line block, the loads of the output
+        // points issued between the arithmetic of the H points, so that shared-memory latency and FP64 work overlap
+        // inside a warp as well as between warps.  Warp TY (the extra column) keeps the two-phase code below.
+        if (SP && tile_plain && roleD && t >= 2 && t <= Th && k0 + 2 * t - 4 >= 1 && k0 + 2 * t - 1 <= Nz - 2 && 2 * t - 3 < n) {
+            const C czA = lds_at<0>(sC1 + (unsigned)(2 * t) * CS, C{}), czB = lds_at<CS>(sC1 + (unsigned)(2 * t) * CS, C{});
+            const C dzA = lds_at<0>(sC2 + (unsigned)(2 * t - 4) * CS, C{}), dzB = lds_at<CS>(sC2 + (unsigned)(2 * t - 4) * CS, C{});
+            T gA0 = Z, gA1 = Z, gA2 = Z, gB0 = Z, gB1 = Z, gB2 = Z;
+            if (ADD) {
+                gA0 = ldg_plain(p.G[0] + off_out); gA1 = ldg_plain(p.G[1] + off_out); gA2 = ldg_plain(p.G[2] + off_out);
+                gB0 = ldg_plain(p.G[0] + off_out + sz); gB1 = ldg_plain(p.G[1] + off_out + sz); gB2 = ldg_plain(p.G[2] + off_out + sz);
+            }
+            mbar_wait(bar_efull + 8 * st_cur, e_phase);  // pair P_t has landed
+            const unsigned aA = sE + st_prev * EPAIR + EPLANE + a_q, aB = sE + st_cur * EPAIR + a_q, aC = aB + EPLANE;
+            const unsigned out = a_out + h_wr;
+            const unsigned hA = sH + (h_wr ^ (2u * HSTAGE)) + b_q, hB = hA + HSTAGE;
+            // E operands of the two H points
+            const T xB = lds_at<0>(aB, T{}), yB = lds_at<ECB>(aB, T{});
+            const T zA = lds_at<2 * ECB>(aA, T{});
+            const T xynA = lds_at<0>(aA + e_dyb, T{}), zynA = lds_at<2 * ECB>(aA + e_dyb, T{});
+            const T yxnA = lds_at<ECB>(aA + e_dxb, T{}), zxnA = lds_at<2 * ECB>(aA + e_dxb, T{});
+            const T xC = lds_at<0>(aC, T{}), yC = lds_at<ECB>(aC, T{});
+            const T zB = lds_at<2 * ECB>(aB, T{});
+            const T xynB = lds_at<0>(aB + e_dyb, T{}), zynB = lds_at<2 * ECB>(aB + e_dyb, T{});
+            const T yxnB = lds_at<ECB>(aB + e_dxb, T{}), zxnB = lds_at<2 * ECB>(aB + e_dxb, T{});
+            {   // H slot 2t−1
+                const T a0 = mul(czA, sub(xB, axlo)), a1 = mul(czA, sub(yB, aylo));
+                const T a2 = mul(ca.cys, sub(xynA, axlo)), a3 = mul(ca.cys, sub(zynA, zA));
+                const T a4 = mul(ca.cxs, sub(yxnA, aylo)), a5 = mul(ca.cxs, sub(zxnA, zA));
+                sts_at<0>(out, add(add(Z, neg(a1)), a3));
+                sts_at<HCB>(out, add(a0, neg(a5)));
+                sts_at<2 * HCB>(out, add(neg(a2), a4));
+            }
+            // H operands of output 2t−4 (pair written in iteration t−1)
+            const T hxA = lds_at<0>(hA, T{}), hyA = lds_at<HCB>(hA, T{}), hzA = lds_at<2 * HCB>(hA, T{});
+            const T hxynA = lds_at<0>(hA + h_dyb, T{}), hzynA = lds_at<2 * HCB>(hA + h_dyb, T{});
+            const T hyxnA = lds_at<HCB>(hA + h_dxb, T{}), hzxnA = lds_at<2 * HCB>(hA + h_dxb, T{});
+            {   // H slot 2t
+                const T b0 = mul(czB, sub(xC, xB)), b1 = mul(czB, sub(yC, yB));
+                const T b2 = mul(ca.cys, sub(xynB, xB)), b3 = mul(ca.cys, sub(zynB, zB));
+                const T b4 = mul(ca.cxs, sub(yxnB, yB)), b5 = mul(ca.cxs, sub(zxnB, zB));
+                sts_at<HSTAGE>(out, add(add(Z, neg(b1)), b3));
+                sts_at<HSTAGE + HCB>(out, add(b0, neg(b5)));
+                sts_at<HSTAGE + 2 * HCB>(out, add(neg(b2), b4));
+            }
+            axlo = xC;
+            aylo = yC;
+            // H operands of output 2t−3
+            const T hxB = lds_at<0>(hB, T{}), hyB = lds_at<HCB>(hB, T{}), hzB = lds_at<2 * HCB>(hB, T{});
+            const T hxynB = lds_at<0>(hB + h_dyb, T{}), hzynB = lds_at<2 * HCB>(hB + h_dyb, T{});
+            const T hyxnB = lds_at<HCB>(hB + h_dxb, T{}), hzxnB = lds_at<2 * HCB>(hB + h_dxb, T{});
+            {   // output 2t−4
+                const T a0 = mul(dzA, sub(hxA, bxlo)), a1 = mul(dzA, sub(hyA, bylo));
+                const T a2 = mul(cb.cys, sub(hxynA, hxA)), a3 = mul(cb.cys, sub(hzynA, hzA));
+                const T a4 = mul(cb.cxs, sub(hyxnA, hyA)), a5 = mul(cb.cxs, sub(hzxnA, hzA));
+                stg_stream(p.G[0] + off_out, ADD ? add(add(gA0, neg(a1)), a3) : add(add(Z, neg(a1)), a3));
+                stg_stream(p.G[1] + off_out, ADD ? add(add(gA1, a0), neg(a5)) : add(a0, neg(a5)));
+                stg_stream(p.G[2] + off_out, ADD ? add(add(gA2, neg(a2)), a4) : add(neg(a2), a4));
+            }
+            {   // output 2t−3
+                const T b0 = mul(dzB, sub(hxB, hxA)), b1 = mul(dzB, sub(hyB, hyA));
+                const T b2 = mul(cb.cys, sub(hxynB, hxB)), b3 = mul(cb.cys, sub(hzynB, hzB));
+                const T b4 = mul(cb.cxs, sub(hyxnB, hyB)), b5 = mul(cb.cxs, sub(hzxnB, hzB));
+                stg_stream(p.G[0] + off_out + sz, ADD ? add(add(gB0, neg(b1)), b3) : add(add(Z, neg(b1)), b3));
+                stg_stream(p.G[1] + off_out + sz, ADD ? add(add(gB1, b0), neg(b5)) : add(b0, neg(b5)));
+                stg_stream(p.G[2] + off_out + sz, ADD ? add(add(gB2, neg(b2)), b4) : add(neg(b2), b4));
+            }
+            bxlo = hxB;
+            bylo = hyB;
+            off_out += 2 * sz;
+            st_prev = st_cur;
+            if (++st_cur == NP) { st_cur = 0; e_phase ^= 1u; }
+            h_wr ^= 2u * HSTAGE;
+            __syncthreads();
+            continue;
+        }
         if (t <= Th) {
             const int hkA = hb + 2 * t - 1;
             const int zfA = zflags_h(hkA), zfB = zflags_h(hkA + 1);

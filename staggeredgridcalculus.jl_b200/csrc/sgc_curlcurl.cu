@@ -47,6 +47,20 @@ int encode_component(CUtensorMap *tm, const cplx *base, int Nx, int Ny, int Nz, 
     return SGC_OK;
 }
 
+// the whole ComplexF64 field (Nx, Ny, Nz, 3) as a 4-D tensor of Float64 pairs; box = (TX+2) x (TY+2) x 2 planes x 3 components
+int encode_field4(CUtensorMap *tm, const cplx *base, int Nx, int Ny, int Nz, int box_x, int box_y) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return sgc_fail(SGC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[4] = {(cuuint64_t)2 * Nx, (cuuint64_t)Ny, (cuuint64_t)Nz, 3};
+    const cuuint64_t strides[3] = {(cuuint64_t)Nx * 16, (cuuint64_t)Nx * Ny * 16, (cuuint64_t)Nx * Ny * Nz * 16};
+    const cuuint32_t box[4] = {(cuuint32_t)2 * box_x, (cuuint32_t)box_y, 2, 3};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return sgc_fail(SGC_ERR_CUDA, "cuTensorMapEncodeTiled (4-D) failed (CUresult %d)", (int)r);
+    return SGC_OK;
+}
+
 template <typename C, bool ADD, int TY, int SE, int SH, bool FZ1, bool FZ2>
 int launch_cc4_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = cc4_smem_bytes(TY, SE, SH);
@@ -99,27 +113,27 @@ int launch_cc5_tiles(const CurlCurl4Params<C> &P, int ty, int se, dim3 grid, cud
 }
 
 // ---- sixth generation (sgc_cc6.cuh): two planes per barrier interval; C₁ forward / C₂ backward in z only ----------------
-template <typename C, bool ADD, int TY, int NP, int MINB>
+template <typename C, bool ADD, int TY, int NP, int MINB, bool SP>
 int launch_cc6_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = cc6_smem_bytes(TY, NP);
-    auto kern = k_cc6<C, ADD, TY, NP, MINB>;
+    auto kern = k_cc6<C, ADD, TY, NP, MINB, SP>;
     static std::atomic<uint64_t> attr_devices{0};
     CUDA_TRY(sgc_set_dynamic_smem(kern, smem, attr_devices));
     kern<<<grid, dim3(32 * (TY + 1), 1, 1), smem, st>>>(P);
     return SGC_OK;
 }
+// sp: software-pipelined steady state
 template <typename C, bool ADD>
-int launch_cc6_tiles(const CurlCurl4Params<C> &P, int ty, int np, dim3 grid, cudaStream_t st) {
-#define CC6_CASE(TY, NP, MINB) if (ty == TY && np == NP) return launch_cc6_one<C, ADD, TY, NP, MINB>(P, grid, st);
-    CC6_CASE(5, 3, 2)
+int launch_cc6_tiles(const CurlCurl4Params<C> &P, int ty, int np, int sp, dim3 grid, cudaStream_t st) {
+#define CC6_CASE(TY, NP, MINB, SP) if (ty == TY && np == NP && sp == SP) return launch_cc6_one<C, ADD, TY, NP, MINB, SP != 0>(P, grid, st);
+    CC6_CASE(5, 3, 2, 1)
 #ifdef SGC_SWEEP_BUILD
-    CC6_CASE(4, 4, 2)
-    CC6_CASE(4, 3, 2)
-    CC6_CASE(11, 3, 1)
-    CC6_CASE(9, 4, 1)
+    CC6_CASE(5, 3, 2, 0)
+    CC6_CASE(11, 3, 1, 1)
+    CC6_CASE(4, 4, 2, 1)
 #endif
 #undef CC6_CASE
-    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v6): tile 32x%d with %d pair stages is not built", ty, np);
+    return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v6): tile 32x%d with %d pair stages, pipelining %d is not built", ty, np, sp);
 }
 
 // z-march that fills whole waves of one-CTA-per-SM: among the chunk counts with a march of at least 16 planes, the
@@ -260,12 +274,14 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
                 CurlCurl4Params<C> P{};
                 P.q = p;
                 int s6 = SGC_OK;
-                for (int d = 0; d < 3 && !s6; ++d) s6 = encode_component(&P.tm[d], p.F[d], p.Nx, p.Ny, p.Nz, 34, ty6 + 2);
+                s6 = encode_field4(&P.tm[0], p.F[0], p.Nx, p.Ny, p.Nz, 34, ty6 + 2);
                 if (!s6) {
                     P.q.march = std::min<int>(c2->march > 0 ? c2->march : 32, CC6_MAXMARCH);
                     dim3 g6((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty6 - 1) / ty6), (unsigned)((nk + P.q.march - 1) / P.q.march));
                     if (g6.y > 65535 || g6.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
-                    s6 = add_mode ? launch_cc6_tiles<C, true>(P, ty6, np6, g6, st) : launch_cc6_tiles<C, false>(P, ty6, np6, g6, st);
+                    // variant bits 8-11: 0 = default (software-pipelined steady state), 1 = two-phase code only
+                    const int sp6 = ((c2->variant >> 8) & 0xF) == 1 ? 0 : 1;
+                    s6 = add_mode ? launch_cc6_tiles<C, true>(P, ty6, np6, sp6, g6, st) : launch_cc6_tiles<C, false>(P, ty6, np6, sp6, g6, st);
                     if (s6) return s6;
                     return sgc_check_launch("k_cc6");
                 }
