@@ -701,6 +701,10 @@ def main():
         out["assembly"] = asm_part
     if cfg5 is not None:
         out["cfg5"] = cfg5
+    if other is not None and "curlcurl_fused" in other:  # the step as one launch: next to the headline it accelerates
+        out["curlcurl_fused"] = other.pop("curlcurl_fused")
+        if parity is not None and not out["curlcurl_fused"].get("bit_identical_to_two_launches", False):
+            parity["ok"] = False
     out["parity"] = parity
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
@@ -864,10 +868,19 @@ def bench_other_configs(S, torch, peak, c_dual, c_prim, E, E2, ms_two_curls):
     r4 = lambda x: round(float(x), 4)
     try:
         M = NLOCAL[0] * NLOCAL[1] * NLOCAL[2]
-        ms = _time(torch, lambda: c_prim.apply_after(c_dual, E2, E, "="))
-        res["curlcurl_fused"] = {"what": "E' = C_prim(C_dual E) in ONE kernel, H kept in shared memory (bit-identical to the two launches)",
-                                 "ms": r4(ms), "ms_two_launches": r4(ms_two_curls), "gcell_updates_per_s": r4(2 * M / ms / 1e6),
-                                 "frac_of_96B_per_cell": r4(96 * M / ms / 1e6 / peak)}
+        # the same step (BASELINE configs[1]: E -> H -> E') as ONE kernel: H lives in shared memory only, so a cell costs
+        # 96 B instead of 192.  Checked here against the two-launch result of the same operators (which the parity leg
+        # compared with the C restatement of the reference): the fused kernel must reproduce it bit for bit.
+        Href, Gref = S.DeviceArray.zeros(NLOCAL + (3,)), S.DeviceArray.zeros(NLOCAL + (3,))
+        c_dual.apply(Href, E, "="); c_prim.apply(Gref, Href, "=")
+        c_prim.apply_after(c_dual, E2, E, "=")
+        same = bool(torch.equal(torch.view_as_real(E2.t), torch.view_as_real(Gref.t)))
+        del Href, Gref
+        ms = _time(torch, lambda: c_prim.apply_after(c_dual, E2, E, "="), iters=50, warm=5)
+        res["curlcurl_fused"] = {"what": "E' = C_prim(C_dual E) in ONE launch of k_cc6 (TMA-fed, two z-planes per barrier interval), H kept in shared memory",
+                                 "ms": r4(ms), "ms_two_launches": r4(ms_two_curls), "speedup": r4(ms_two_curls / ms),
+                                 "gcell_updates_per_s": r4(2 * M / ms / 1e6), "achieved_gbs_96B_per_cell": r4(96 * M / ms / 1e6),
+                                 "frac_of_96B_per_cell": r4(96 * M / ms / 1e6 / peak), "bit_identical_to_two_launches": same}
         N3 = NLOCAL
         rng = np.random.default_rng(3)
         d3 = [rng.uniform(0.5, 1.5, n) + 1j * rng.uniform(-.2, .2, n) for n in N3]

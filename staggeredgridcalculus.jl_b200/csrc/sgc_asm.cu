@@ -356,7 +356,9 @@ extern "C" int sgc_asm_set_col_range(sgc_asm *a, int64_t col_begin, int64_t col_
 
 extern "C" int sgc_asm_set_tuning(sgc_asm *a, int force_count_pass) {
     REQUIRE(a, "handle is NULL");
-    a->force_count_pass = force_count_pass != 0;
+    a->force_count_pass = (force_count_pass & 1) != 0;
+    a->no_fast = (force_count_pass & 2) != 0;
+    a->no_warp = (force_count_pass & 4) != 0;
     a->nnz = -1;
     a->counted = false;
     return SGC_OK;
@@ -369,6 +371,8 @@ extern "C" int sgc_asm_shape(const sgc_asm *a, int64_t *m, int64_t *n, int *val_
     if (val_dtype) *val_dtype = a->cx ? SGC_C128 : SGC_F64;
     return SGC_OK;
 }
+
+static int asm_slots_per_col(const sgc_asm *a);
 
 template <typename T>
 static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
@@ -413,6 +417,37 @@ static AsmParams<T> asm_params(const sgc_asm *a, int index_base) {
         p.col_base = a->col_begin;
         p.entry_base = a->entry_base;
     }
+    // interior fast path: per block column the entries in ascending row order (valid where nothing wraps or drops)
+    p.fast_enabled = 0;
+    {
+        const int E = asm_slots_per_col(a);
+        bool ok = p.prefix_enabled && E > 0 && !a->no_fast;
+        for (int nu = 0; nu < a->Kin && ok; ++nu) ok = (2 * p.nblk_of[nu] == E);
+        for (int b = 0; b < p.nblk && ok; ++b) ok = (a->blocks[b].ns != 0) && (a->N[a->blocks[b].axis] >= 3);
+        if (ok) {
+            const int64_t stride[3] = {1, a->N[0], a->N[0] * a->N[1]};
+            for (int nu = 0; nu < a->Kin; ++nu) {
+                struct Ent { int64_t key; const T *V; int axis, dsub; };
+                std::vector<Ent> ents;
+                for (int q = 0; q < p.nblk_of[nu]; ++q) {
+                    const AsmBlock<T> &B = p.blk[p.blk_of[nu][q]];
+                    const int64_t delta = -(int64_t)B.ns * stride[B.axis];
+                    auto key = [&](int64_t d) { return a->cmpfirst ? (int64_t)a->Kout * d + B.nv : d + a->M * (int64_t)B.nv; };
+                    ents.push_back({key(0), B.V0, B.axis, 0});
+                    ents.push_back({key(delta), B.Vs, B.axis, -B.ns});
+                }
+                std::stable_sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) { return x.key < y.key; });
+                for (size_t e = 0; e + 1 < ents.size(); ++e) ok = ok && (ents[e].key != ents[e + 1].key);
+                for (size_t e = 0; e < ents.size() && e < (size_t)ASM_MAX_ENTRIES; ++e)
+                    p.fast[nu][e] = AsmFastEntry<T>{ents[e].V, ents[e].key, ents[e].axis, ents[e].dsub};
+            }
+            for (int d = 0; d < 3; ++d) {
+                p.in_lo[d] = a->N[d] >= 3 ? 1u : 0u;
+                p.in_span[d] = a->N[d] >= 3 ? (unsigned)(a->N[d] - 3) : (unsigned)(a->N[d] - 1);
+            }
+            p.fast_enabled = ok ? 1 : 0;
+        }
+    }
     int64_t before = 0;
     for (int set = 0; set < 4; ++set) {
         for (int ax = 0; ax < 3; ++ax) p.prefix[set][ax] = a->prefix_tables + a->prefix_off[set][ax];
@@ -438,6 +473,14 @@ static int asm_launch(const sgc_asm *a, int index_base, const int64_t *colptr_in
                       T *nzval, cudaStream_t st) {
     AsmParams<T> p = asm_params<T>(a, index_base);
     if (a->ncta == 0) return SGC_OK;
+    if (MODE == ASM_FILL_ALL && p.prefix_enabled && !a->no_warp) {
+        // closed-form offsets: warp-granular kernel (no CTA-wide barrier, no block scan)
+        const size_t smem = (sizeof(T) + sizeof(R)) * (size_t)ASM_BLOCK * (NCOLS * E + 1);
+        auto kern = k_asm_warp<T, IDX, R, ASM_BLOCK, NCOLS, E>;
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)a->ncta, ASM_BLOCK, smem, st>>>(p, colptr_out, rowval, nzval);
+        return check_launch("k_asm_warp");
+    }
     const bool needs_smem = (MODE == ASM_FILL || MODE == ASM_FILL_ALL);
     const size_t smem = needs_smem ? (sizeof(T) + sizeof(R)) * (size_t)ASM_BLOCK * (NCOLS * E + 1) : 0;
     auto kern = k_asm_group<T, IDX, R, ASM_BLOCK, MODE, NCOLS, E>;

@@ -32,6 +32,16 @@ struct AsmBlock {
     int ns;         // +1 forward, -1 backward, 0: diagonal-only block (permutation)
 };
 
+// One entry of a column whose cell lies in the interior of the grid (no wrap-around, nothing dropped), in ascending
+// row order: row = (Kout·c | c) + rowadd, value = V[sub[axis] + dsub].  The order of a column's entries only depends
+// on the blocks' shifts and component positions there, so the host sorts them once (sgc_asm.cu: asm_params).
+template <typename T>
+struct AsmFastEntry {
+    const T *V;
+    int64_t rowadd;
+    int axis, dsub;
+};
+
 template <typename T>
 struct AsmParams {
     AsmBlock<T> blk[ASM_MAX_BLOCKS];
@@ -62,6 +72,10 @@ struct AsmParams {
     int64_t set_base[4];          // entries before the first group of the set
     // column partition: groups [cta_first·BLOCK, g_end) are processed; outputs are re-based to the block
     int64_t cta_first, g_end, col_base, entry_base;
+    // interior cells of CTAs whose columns are all full: entries straight from the host-sorted descriptors
+    int fast_enabled;
+    unsigned in_lo[3], in_span[3];  // interior ⇔ sub[a] − in_lo[a] ≤ in_span[a] (unsigned) on every axis
+    AsmFastEntry<T> fast[3][ASM_MAX_ENTRIES];
 };
 
 // entries stored before group g (= before its first column) when all rows are kept
@@ -310,6 +324,10 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
     // staged, ranked instead of moved — 56 instead of 96 registers for ComplexF64.
     constexpr bool LATE = sizeof(T) > 8;
     constexpr bool HOLD = WRITES && !LATE;
+    // closed-form offsets available (all rows kept): the counts come from the separable tables for every value type, and
+    // CTAs whose columns are all full emit the entries of interior cells from the host-sorted descriptors (p.fast) —
+    // no block walk, no zero / range tests, no sorting; cells on a grid face keep the general path
+    const bool hold = HOLD && !p.fast_enabled;
     int cnt[NCOLS];
     R hrows[HOLD ? NCOLS : 1][E];
     T hvals[HOLD ? NCOLS : 1][E];
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
     for (int q = 0; q < NCOLS; ++q) {
         cnt[q] = 0;
         if (live) {
-            if (HOLD) {
+            if (HOLD && hold) {
                 int rk[E];
                 cnt[q] = column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, hrows[HOLD ? q : 0], hvals[HOLD ? q : 0], rk);
             } else if (p.prefix_enabled) {
@@ -362,9 +380,20 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             T *s_vals = reinterpret_cast<T *>(smem_raw);
             R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)SLOTS);
             const int s0 = threadIdx.x * (PADK + 1);
+            const bool fast = p.fast_enabled && ((unsigned)sub[0] - p.in_lo[0] <= p.in_span[0]) && ((unsigned)sub[1] - p.in_lo[1] <= p.in_span[1]) &&
+                              ((unsigned)sub[2] - p.in_lo[2] <= p.in_span[2]);
+            const R rowbase = p.cmpfirst ? (R)p.Kout * (R)c : (R)c;
 #pragma unroll
             for (int q = 0; q < NCOLS; ++q) {
-                if (HOLD) {
+                if (fast) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const AsmFastEntry<T> &f = p.fast[nu0 + q][e];
+                        const int64_t at = (int64_t)(f.axis == 0 ? sub[0] : (f.axis == 1 ? sub[1] : sub[2])) + f.dsub;
+                        s_rows[s0 + q * E + e] = rowbase + (R)f.rowadd;
+                        s_vals[s0 + q * E + e] = f.V[at];
+                    }
+                } else if (HOLD && hold) {
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         s_rows[s0 + q * E + e] = hrows[HOLD ? q : 0][e];
@@ -419,7 +448,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             int o = off0;
 #pragma unroll
             for (int q = 0; q < NCOLS; ++q) {
-                if (HOLD) {
+                if (HOLD && hold) {
 #pragma unroll
                     for (int e = 0; e < E; ++e)
                         if (e < cnt[q]) {
@@ -451,6 +480,132 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
             rowval[base + q] = (int64_t)s_rows[slot] + ib;
             stg_stream(nzval + base + q, s_vals[slot]);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-granular one-pass assembly for the closed-form case (all rows kept; also a block of columns).
+// The closed form gives the output offset of ANY group, so nothing couples the warps of a CTA: each warp takes 32
+// consecutive groups, derives its own base offset, and stages its entries in a private slice of shared memory —
+// no CTA-wide barrier, no block scan (k_asm_group: 3 barriers per CTA, 22 % of its stall samples).  A warp whose
+// columns are all full (`__all_sync`) writes an arithmetic colptr and emits interior cells from the host-sorted
+// descriptors; any other warp runs the general entry path behind an intra-warp shuffle scan.
+// ---------------------------------------------------------------------------------------------
+template <typename T, typename IDX, typename R, int BLOCK, int NCOLS, int E>
+__global__ void __launch_bounds__(BLOCK) k_asm_warp(const __grid_constant__ AsmParams<T> p, int64_t *__restrict__ colptr_out,
+                                                    int64_t *__restrict__ rowval, T *__restrict__ nzval) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int PADK = NCOLS * E;
+    constexpr int WSLOTS = 32 * (PADK + 1);
+    constexpr int NWARP = BLOCK / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T *s_vals = reinterpret_cast<T *>(smem_raw) + wid * WSLOTS;
+    R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)WSLOTS * NWARP) + wid * WSLOTS;
+    const int64_t g0 = ((int64_t)blockIdx.x + p.cta_first) * BLOCK + wid * 32;  // the warp's first group
+    if (g0 >= p.g_end) return;
+    const int64_t g = g0 + lane;
+    const bool live = g < p.g_end;
+    int nu0 = 0;
+    IDX c = 0, sub[3] = {0, 0, 0};
+    if (live) group_decode<T, IDX>(p, g, nu0, c, sub);
+    int cnt[NCOLS];
+    int mine = 0;
+#pragma unroll
+    for (int q = 0; q < NCOLS; ++q) {
+        cnt[q] = live ? p.cnt_tab[nu0 + q][0][sub[0]] + p.cnt_tab[nu0 + q][1][sub[1]] + p.cnt_tab[nu0 + q][2][sub[2]] : 0;
+        mine += cnt[q];
+    }
+    const int64_t ib = p.index_base;
+    const int64_t base = prefix_entries_before<T, IDX>(p, g0) - p.entry_base;
+    const int64_t col0 = g0 * NCOLS - p.col_base;
+    const int64_t ncol_out = p.g_end * NCOLS - p.col_base;
+    if (__all_sync(0xffffffffu, mine == PADK)) {
+        // ---- every column of the warp holds exactly E entries ----------------------------------------------------
+#pragma unroll
+        for (int q = 0; q < NCOLS; ++q) {
+            const int cc = lane + q * 32;
+            colptr_out[col0 + cc] = base + ib + (int64_t)E * cc;
+        }
+        if (g == p.g_end - 1) colptr_out[ncol_out] = base + ib + 32 * PADK;
+        const int s0 = lane * (PADK + 1);
+        const bool fast = p.fast_enabled && ((unsigned)sub[0] - p.in_lo[0] <= p.in_span[0]) && ((unsigned)sub[1] - p.in_lo[1] <= p.in_span[1]) &&
+                          ((unsigned)sub[2] - p.in_lo[2] <= p.in_span[2]);
+        if (fast) {
+            const R rowbase = p.cmpfirst ? (R)p.Kout * (R)c : (R)c;
+#pragma unroll
+            for (int q = 0; q < NCOLS; ++q) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const AsmFastEntry<T> &f = p.fast[nu0 + q][e];
+                    const int64_t at = (int64_t)(f.axis == 0 ? sub[0] : (f.axis == 1 ? sub[1] : sub[2])) + f.dsub;
+                    s_rows[s0 + q * E + e] = rowbase + (R)f.rowadd;
+                    s_vals[s0 + q * E + e] = f.V[at];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < NCOLS; ++q) {
+                R rows[E];
+                T vals[E];
+                int rank[E];
+                column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows, vals, rank);
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int slot = s0 + q * E + rank[e];
+                    s_rows[slot] = rows[e];
+                    s_vals[slot] = vals[e];
+                }
+            }
+        }
+        __syncwarp();
+        int64_t *rv = rowval + base + lane;
+        T *nz = nzval + base + lane;
+#pragma unroll
+        for (int it = 0; it < PADK; ++it) {
+            const int q = lane + it * 32;
+            const int slot = q + q / PADK;
+            rv[it * 32] = (int64_t)s_rows[slot] + ib;
+            stg_stream(nz + it * 32, s_vals[slot]);
+        }
+        return;
+    }
+    // ---- general warp: entries dropped at a symmetric face, duplicates on an axis of length 1, or a ragged end ----
+    int incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    const int off0 = incl - mine;
+    if (live) {
+        int64_t o = base + off0 + ib;
+        int at0 = off0;
+#pragma unroll
+        for (int q = 0; q < NCOLS; ++q) {
+            colptr_out[col0 + (int64_t)lane * NCOLS + q] = o;
+            o += cnt[q];
+            R rows[E];
+            T vals[E];
+            int rank[E];
+            column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows, vals, rank);
+#pragma unroll
+            for (int e = 0; e < E; ++e)
+                if (rank[e] < cnt[q]) {  // valid entries rank before the invalid ones
+                    const int at = at0 + rank[e];
+                    const int slot = at + at / PADK;
+                    s_rows[slot] = rows[e];
+                    s_vals[slot] = vals[e];
+                }
+            at0 += cnt[q];
+        }
+        if (g == p.g_end - 1) colptr_out[ncol_out] = o;  // one-past-the-end entry
+    }
+    __syncwarp();
+    for (int q = lane; q < total; q += 32) {
+        const int slot = q + q / PADK;
+        rowval[base + q] = (int64_t)s_rows[slot] + ib;
+        stg_stream(nzval + base + q, s_vals[slot]);
     }
 }
 

@@ -155,6 +155,23 @@ int cc4_march(int64_t tiles, int64_t nk) {
     return best_march;
 }
 
+// z-march of the sixth generation (two CTAs per SM): an even number of planes between 24 and 48 whose last wave is
+// fullest, weighted by the z-halo overhead (m + 2 planes computed for m written); measured flat within 1.5 % over 20 … 52
+int cc6_march(int64_t tiles, int64_t nk) {
+    if (nk <= 48) return (int)nk;
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    double best = -1.0;
+    int best_march = 32;
+    for (int m = 24; m <= 48; m += 2) {
+        const double waves = (double)(tiles * ((nk + m - 1) / m)) / (2.0 * sms);
+        const double eff = waves / std::ceil(waves) * ((double)m / (m + 2));
+        if (eff > best + 1e-9) { best = eff; best_march = m; }
+    }
+    return best_march;
+}
+
 template <typename T, typename C, bool ADD, int TX, int TY, int SE, int MINB>
 int launch_cc_one(const CurlCurlParams<T, C> &p, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = ((size_t)SE * 3 * (TX + 2) * (TY + 2) + (size_t)3 * 3 * (TX + 1) * (TY + 1)) * sizeof(T);
@@ -250,7 +267,8 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
     p.c1z_hi = narrow_c<C>(c1->cz_ghost[1]);
     p.Nx = (int)c1->N[0]; p.Ny = (int)c1->N[1]; p.Nz = (int)c1->N[2];
     p.k_begin = (int)k_begin; p.k_end = (int)k_end;
-    // variant bits 0-3: 0 = warp-role kernel (default), 1 = first generation (two-pass H positions)
+    // variant bits 0-3: 0 = default (sixth generation where it applies, else the third), 2 = third generation (warp roles),
+    // 1 = first generation (two-pass H positions), 4 / 5 / 6 = k_cc4 / k_cc5 / k_cc6 where they apply
     const int version = c2->variant & 0xF;
     const int tx = (version == 1 && c2->tile_x) ? c2->tile_x : 32;
     const int ty = c2->tile_y ? c2->tile_y : (version == 1 ? 8 : 7);  // 32x7 outputs + 1 halo row = 8 warps, 2 CTAs/SM at 128 registers
@@ -267,16 +285,19 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
         int ty4 = (c2->tile_y == 8) ? 8 : 6;
         const bool wraps_xy = a1.bloch[0] || a1.bloch[1] || a2.bloch[0] || a2.bloch[1];
         const bool ghosts = (ghost_lo && ghost_lo[0]) || (ghost_hi && ghost_hi[0]) || c1->lo_iface || c1->hi_iface;
-        if (version == 6 && !wraps_xy && !ghosts && !a1.bloch[2] && !a2.bloch[2] && a1.fwd[2] && !a2.fwd[2] && p.Nx >= 34) {
+        // sixth generation (sgc_cc6.cuh) — the DEFAULT where it applies: all-symmetric box, C₁ forward / C₂ backward in z,
+        // no slab ghost planes, a grid that holds a whole tile
+        const bool v6_ok = !wraps_xy && !ghosts && !a1.bloch[2] && !a2.bloch[2] && a1.fwd[2] && !a2.fwd[2] && p.Nx >= 34;
+        if (v6_ok && (version == 6 || (version == 0 && (c2->tile_y == 0 || c2->tile_y == 5)))) {
             const int ty6 = c2->tile_y ? c2->tile_y : 5;
             const int np6 = ((c2->variant >> 4) & 0xF) ? ((c2->variant >> 4) & 0xF) : 3;
             if (p.Ny >= ty6 + 2) {
                 CurlCurl4Params<C> P{};
                 P.q = p;
-                int s6 = SGC_OK;
-                s6 = encode_field4(&P.tm[0], p.F[0], p.Nx, p.Ny, p.Nz, 34, ty6 + 2);
+                int s6 = encode_field4(&P.tm[0], p.F[0], p.Nx, p.Ny, p.Nz, 34, ty6 + 2);
                 if (!s6) {
-                    P.q.march = std::min<int>(c2->march > 0 ? c2->march : 32, CC6_MAXMARCH);
+                    const int64_t tiles6 = (int64_t)((p.Nx + 31) / 32) * ((p.Ny + ty6 - 1) / ty6);
+                    P.q.march = c2->march > 0 ? std::min<int>(c2->march, CC6_MAXMARCH) : cc6_march(tiles6, nk);
                     dim3 g6((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty6 - 1) / ty6), (unsigned)((nk + P.q.march - 1) / P.q.march));
                     if (g6.y > 65535 || g6.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
                     // variant bits 8-11: 0 = default (software-pipelined steady state), 1 = two-phase code only
@@ -285,6 +306,7 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
                     if (s6) return s6;
                     return sgc_check_launch("k_cc6");
                 }
+                // no tensor-map support in this driver: fall through to the third generation
             }
         }
         if (version == 5 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= 9) {

@@ -93,6 +93,8 @@ struct sgc_asm {
     size_t prefix_off[4][3] = {};             // element offsets into prefix_tables
     int64_t set_total[4] = {0, 0, 0, 0};      // entries of each set when all rows are kept
     bool force_count_pass = false;            // testing: use the count kernel + device scan even when the closed form applies
+    bool no_fast = false;                     // testing: interior cells take the general entry path too
+    bool no_warp = false;                     // testing: the CTA-granular kernel (block scan) even where the closed form applies
     // column partition (sgc_asm_set_col_range): the block of columns [col_begin, col_end) as a stand-alone CSC matrix
     int64_t col_begin = 0, col_end = -1;      // -1: all columns
     int64_t cta_first = 0;                    // first CTA (of the whole-matrix launch) of the column range

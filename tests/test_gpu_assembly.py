@@ -84,7 +84,7 @@ def test_create_curl_matches_oracle(S, N, isfwd):
     for dl, isbloch, ee in cases:
         for cmpfirst in (True, False):
             ref = O.create_curl(isfwd, dl, isbloch, ee, N=N if dl is None else None, order_cmpfirst=cmpfirst)
-            for method in ("direct", "counted", "twostep", "coo"):
+            for method in ("direct", "general", "cta", "counted", "twostep", "coo"):
                 got = S.create_curl(isfwd, dl, isbloch, ee, N=N, order_cmpfirst=cmpfirst, method=method)
                 assert_csc_equal(got, ref, f"create_curl N={N} fwd={isfwd} bloch={isbloch} cmpfirst={cmpfirst} {method}")
 
@@ -128,6 +128,36 @@ def test_create_subcurls_divg_grad_picmp_match_oracle(S):
                 assert_csc_equal(S.create_picmp((3, 4), [3, 1, 2], scale=scale, order_cmpfirst=cmpfirst, method=method),
                                  O.create_picmp((3, 4), [3, 1, 2], scale=scale, order_cmpfirst=cmpfirst),
                                  f"πcmp cmpfirst={cmpfirst} scale={scale} {method}")
+
+
+@pytest.mark.parametrize("N", [(140, 9, 7), (33, 40, 5), (130, 3, 3)])
+def test_interior_descriptor_path_equals_general_path(S, N):
+    """CTAs whose columns are all full emit interior cells from host-sorted descriptors; cells on a grid face and every
+    other CTA walk the blocks and sort.  Both must give the same matrix (and the oracle's) for every operator shape."""
+    rng = np.random.default_rng(77)
+    dl = [rand_coef(rng, n, True) for n in N]
+    e = np.exp(-1j * rng.uniform(0, 3, 3))
+    for isfwd in ([True, False, True], [False, True, False]):
+        for isbloch in ([True] * 3, [True, False, True]):
+            for cmpfirst in (True, False):
+                ref = O.create_curl(isfwd, dl, isbloch, e, order_cmpfirst=cmpfirst)
+                for method in ("direct", "general", "cta"):
+                    got = S.create_curl(isfwd, dl, isbloch, e, N=N, order_cmpfirst=cmpfirst, method=method)
+                    assert_csc_equal(got, ref, f"create_curl N={N} fwd={isfwd} bloch={isbloch} cmpfirst={cmpfirst} {method}")
+            for name, mk, mo in (("divg", S.create_divg, O.create_divg), ("grad", S.create_grad, O.create_grad)):
+                for cmpfirst in (True, False):
+                    ref = mo(isfwd, dl, isbloch, e, order_cmpfirst=cmpfirst)
+                    for method in ("direct", "general", "cta"):
+                        got = mk(isfwd, dl, isbloch, e, order_cmpfirst=cmpfirst, method=method)
+                        assert_csc_equal(got, ref, f"create_{name} N={N} fwd={isfwd} bloch={isbloch} cmpfirst={cmpfirst} {method}")
+            ref = O.create_mean(isfwd, dl, dl, isbloch, e)
+            for method in ("direct", "general", "cta"):
+                assert_csc_equal(S.create_mean(isfwd, dl, dl, isbloch, e, method=method), ref, f"create_mean N={N} {method}")
+            for nw in (1, 2, 3):
+                ref = O.create_partial(nw, isfwd[nw - 1], N, dl[nw - 1], isbloch[nw - 1], e[nw - 1])
+                for method in ("direct", "general", "cta"):
+                    assert_csc_equal(S.create_partial(nw, isfwd[nw - 1], N, dl[nw - 1], isbloch[nw - 1], e[nw - 1], method=method), ref,
+                                     f"create_∂ N={N} nw={nw} {method}")
 
 
 def test_zero_coefficients_are_dropped(S):
