@@ -195,6 +195,48 @@ int sgc_launch_divgrad3(const sgc_op *op, bool is_divg, T *G, const T *F, const 
     return sgc_check_launch(is_divg ? "k_curl3p<DIVG>" : "k_curl3p<GRAD>");
 }
 
+// apply_mean! on 3-D grids through the same staged z-march (k_curl3p MODE = MEAN): one launch instead of three sweeps
+template <typename C> static inline C narrow_mean(cplx v);
+template <> inline double narrow_mean<double>(cplx v) { return v.re; }
+template <> inline cplx narrow_mean<cplx>(cplx v) { return v; }
+
+template <typename T, typename C>
+int sgc_launch_mean3(const sgc_op *op, T *G, const T *F, bool add_mode, int64_t k_begin, int64_t k_end, cudaStream_t st) {
+    if (k_end <= k_begin) return SGC_OK;
+    CurlParams<T, C> p{};
+    const int64_t M = op->M, sz = op->N[0] * op->N[1];
+    const Term *tz = nullptr;
+    for (const Term &t : op->terms) {  // one m̂ term per axis, component d averaged along axis d
+        const int d = t.axis;
+        p.c[d] = (const C *)((const unsigned char *)op->arena + t.off_c);
+        p.m[d].w = (const C *)((const unsigned char *)op->arena + t.off_w);
+        p.m[d].a2 = narrow_mean<C>(t.a2); p.m[d].a1 = narrow_mean<C>(t.a1); p.m[d].b0 = narrow_mean<C>(t.b0);
+        p.m[d].w_hi = narrow_mean<C>(t.w_hi); p.m[d].w_lo = narrow_mean<C>(t.w_lo);
+        p.m[d].weighted = (t.kind == KIND_MEAN_WEIGHTED) ? 1 : 0;
+        p.e[d] = t.e; p.e_real[d] = t.e_real; p.fwd[d] = t.fwd;
+        p.bc_lo[d] = p.bc_hi[d] = t.bloch ? BC_BLOCH : BC_SYM;
+        if (d == 2) tz = &t;
+    }
+    if (!tz) return sgc_fail(SGC_ERR_INVALID, "mean without a z term");
+    // slot 0 = F_z (z-averaged through the register carry), slot 1 = F_x (x-averaged), slot 2 = F_y (y-averaged)
+    p.F[0] = F + 2 * M; p.F[1] = F; p.F[2] = F + M;
+    p.G[0] = G + 2 * M; p.G[1] = G; p.G[2] = G + M;
+    p.ghost[0] = tz->fwd ? p.F[0] : p.F[0] + (op->N[2] - 1) * sz;  // the wrap-around plane
+    p.ghost[1] = p.ghost[0];
+    p.Nx = (int)op->N[0]; p.Ny = (int)op->N[1]; p.Nz = (int)op->N[2];
+    p.k_begin = (int)k_begin; p.k_end = (int)k_end;
+    p.march = 12;
+    const int64_t nk = k_end - k_begin;
+    dim3 grid((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + 3) / 4), (unsigned)((nk + p.march - 1) / p.march));
+    if (grid.y > 65535 || grid.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the staged mean");
+    int s = add_mode ? launch_divgrad_one<T, C, true, CURL3_MEAN>(p, grid, st) : launch_divgrad_one<T, C, false, CURL3_MEAN>(p, grid, st);
+    if (s) return s;
+    return sgc_check_launch("k_curl3p<MEAN>");
+}
+template int sgc_launch_mean3<double, double>(const sgc_op *, double *, const double *, bool, int64_t, int64_t, cudaStream_t);
+template int sgc_launch_mean3<cplx, double>(const sgc_op *, cplx *, const cplx *, bool, int64_t, int64_t, cudaStream_t);
+template int sgc_launch_mean3<cplx, cplx>(const sgc_op *, cplx *, const cplx *, bool, int64_t, int64_t, cudaStream_t);
+
 template int sgc_launch_divgrad3<double, double>(const sgc_op *, bool, double *, const double *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
 template int sgc_launch_divgrad3<cplx, double>(const sgc_op *, bool, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);
 template int sgc_launch_divgrad3<cplx, cplx>(const sgc_op *, bool, cplx *, const cplx *, const void *const *, bool, int64_t, int64_t, cudaStream_t);

@@ -128,6 +128,7 @@ struct sgc_op {
     bool fused_cc = false;
     size_t fused_off[3] = {0, 0, 0};
     int fused_pat = -1;           // PAT_* when the term list is one of the one-launch compositions
+    bool fused_mean = false;      // apply_mean! on a 3-D grid: one launch of the staged z-march (k_curl3p MODE = MEAN)
     int lo_iface = 0, hi_iface = 0;
     // neighbour synchronisation folded into the fused curl kernel (sgc_op_attach_comm, sgc_comm.cu)
     long long *sync_ctrl = nullptr;                  // this rank's control block
@@ -167,6 +168,8 @@ struct OpBuilder {
 template <typename T, typename C>
 int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghost, bool add_mode,
                      int64_t k_begin, int64_t k_end, cudaStream_t st);
+template <typename T, typename C>
+int sgc_launch_mean3(const sgc_op *op, T *G, const T *F, bool add_mode, int64_t k_begin, int64_t k_end, cudaStream_t st);
 template <typename T, typename C>
 int sgc_launch_divgrad3(const sgc_op *op, bool is_divg, T *G, const T *F, const void *const *ghost, bool add_mode,
                         int64_t k_begin, int64_t k_end, cudaStream_t st);

@@ -370,6 +370,17 @@ __global__ void __launch_bounds__(256) k_fill_zero(T *G, int64_t n) {
 enum : int { SGC_CTRL_FLAG_LO = 0, SGC_CTRL_FLAG_HI = 1, SGC_CTRL_EPOCH = 2, SGC_CTRL_TICKETS = 3 /* 2 x uint32 */,
              SGC_CTRL_SIDES_DONE = 4 /* uint32 */, SGC_CTRL_BAR_COUNT = 5, SGC_CTRL_BAR_SLOTS = 8 /* + world */ };
 
+// apply_mean! through the staged z-march (k_curl3p MODE = CURL3_MEAN): the m̂ coefficients of one axis
+// (the fields of TermParams, matrixfree/mean.jl:102-922)
+template <typename C>
+struct MeanAxis {
+    const C *w;        // weighted: ∆w[i]
+    C a2, a1;          // arithmetic: 0.5α, α
+    C b0;              // weighted, backward + symmetric: α·∆w′⁻¹[1]
+    C w_hi, w_lo;      // weighted: ∆w of the plane beyond the upper / lower end (Bloch phase folded into w_hi)
+    int weighted;
+};
+
 template <typename T, typename C>
 struct CurlParams {
     const T *F[3];       // Fx, Fy, Fz  (each Nx*Ny*Nz)
@@ -395,7 +406,42 @@ struct CurlParams {
     long long *sync_ctrl;            // this rank's control block (SGC_CTRL_* slots)
     long long *sync_post[2];         // peer addresses: the lower neighbour's FLAG_HI slot, the upper neighbour's FLAG_LO slot
     int sync_side[2];                // this rank has a neighbour on the lower / upper side
+    MeanAxis<C> m[3];                // MODE = CURL3_MEAN only (c[d] then holds 0.5α·∆w′⁻¹ of a weighted mean)
 };
+
+// m̂ value at a cell that no boundary rule touches (mean.jl:121-125 / :229-233 arithmetic, :516-520 / :633-637 weighted;
+// the forward and backward forms differ only in the order of the two summands, which IEEE addition does not see)
+template <typename T, typename C>
+SGC_D T mean_plain(bool weighted, C a2, C c, C w_cur, C w_nb, T cur, T nb) {
+    if (!weighted) return mul(a2, add(nb, cur));
+    return mul(c, add(mul(w_nb, nb), mul(w_cur, cur)));
+}
+// m̂ value with the boundary rules: the branches and formulas of term_value<…, KIND_MEAN_*> with the operands in
+// registers; `nb` is the RAW neighbour (the wrap-around value at a Bloch face, unused at a symmetric one)
+template <typename T, typename C>
+SGC_D T mean_eval(const CurlParams<T, C> &p, int d, int i, int Nw, T cur, T nb) {
+    const MeanAxis<C> &m = p.m[d];
+    const C *c = p.c[d];
+    const bool W = m.weighted != 0;
+    if (p.fwd[d]) {
+        if (i == Nw - 1) {
+            if (p.bc_hi[d] == BC_SYM) return W ? mul(mul(c[i], m.w[i]), cur) : mul(m.a2, cur);                      // :546-549 / :149-151
+            if (W) return mul(c[i], add(mul(m.w_hi, nb), mul(m.w[i], cur)));                                        // :524-527
+            if (p.bc_hi[d] == BC_BLOCH) return mul(m.a2, add(mul_e(p.e[d], nb, p.e_real[d]), cur));                  // :129-131
+            return mul(m.a2, add(nb, cur));
+        }
+        if (i == 0 && p.bc_lo[d] == BC_SYM) return W ? mul(mul(c[0], m.w[1]), nb) : mul(m.a2, nb);                   // :539-542 / :143-145
+        return W ? mul(c[i], add(mul(m.w[i + 1], nb), mul(m.w[i], cur))) : mul(m.a2, add(nb, cur));
+    }
+    if (i == 0) {
+        if (p.bc_lo[d] == BC_SYM) return W ? mul(mul(m.b0, m.w[0]), cur) : mul(m.a1, cur);                           // :646-650 / :241-245
+        if (p.bc_lo[d] == BC_BLOCH)
+            return W ? mul(c[0], add(mul(m.w[0], cur), div_e(mul(m.w_lo, nb), p.e[d], p.e_real[d])))                 // :641-645
+                     : mul(m.a2, add(cur, div_e(nb, p.e[d], p.e_real[d])));                                          // :237-240
+        return W ? mul(c[0], add(mul(m.w[0], cur), mul(m.w_lo, nb))) : mul(m.a2, add(cur, nb));
+    }
+    return W ? mul(c[i], add(mul(m.w[i], cur), mul(m.w[i - 1], nb))) : mul(m.a2, add(cur, nb));
+}
 
 SGC_D long long ld_acquire_sys(const long long *p) {
     long long v;
@@ -693,7 +739,9 @@ struct CurlCellBC {
 //   CURL3_DIVG  g = ∂xF_x + ∂yF_y + ∂zF_z  (apply_divg!, divergence.jl:41-66): slot 0 = F_z (the z-differenced
 //               slot), slot 1 = F_x (x-differenced), slot 2 = F_y (y-differenced); one output, terms in x,y,z order
 //   CURL3_GRAD  G_w = ∂w f                  (apply_grad!, gradient.jl:41-59): slot 0 = f, differenced along all axes
-enum : int { CURL3_CURL = 0, CURL3_DIVG = 1, CURL3_GRAD = 2 };
+//   CURL3_MEAN  G_w = m̂_w F_w               (apply_mean!, mean.jl:47-89): slots as for the divergence — F_z is averaged along z
+//               through the register carry, F_x along x, F_y along y — and three outputs (G[0] = G_z, G[1] = G_x, G[2] = G_y)
+enum : int { CURL3_CURL = 0, CURL3_DIVG = 1, CURL3_GRAD = 2, CURL3_MEAN = 3 };
 template <typename T, typename C, bool ADD, int TX, int TY, int S, int MINB, bool XSHFL, int MODE = CURL3_CURL>
 __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__ CurlParams<T, C> p) {
     static_assert(TX % 32 == 0, "a warp must lie inside one row");
@@ -702,6 +750,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
     constexpr int PITCH = TX + 1;
     constexpr int COMP = (TY + 1) * PITCH;
     constexpr int STAGE = 3 * COMP;
+    constexpr bool DIVLIKE = (MODE == CURL3_DIVG || MODE == CURL3_MEAN);  // staging of the divergence
     extern __shared__ __align__(16) unsigned char sgc_smem_raw[];
     T *const sm = reinterpret_cast<T *>(sgc_smem_raw);
 
@@ -751,7 +800,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             if (hj < 0) { hj = Ny - 1; ok = (p.bc_lo[1] == BC_BLOCH); }
             if (ok) {
                 hcomp = (lin < TX) ? 0 : 2;  // y-halo row of slot 0 and slot 2
-                if (MODE == CURL3_DIVG && hcomp == 0) hcomp = -1;  // divergence: only slot 2 (F_y) is y-differenced
+                if (DIVLIKE && hcomp == 0) hcomp = -1;  // divergence: only slot 2 (F_y) is y-differenced
                 if (MODE == CURL3_GRAD && hcomp == 2) hcomp = -1;  // gradient: only slot 0 (f)
                 hdst = (fy ? nvy : 0) * PITCH + (x + (fx ? 0 : 1));
                 hsrc = (int64_t)hj * sy + (i0 + x);
@@ -767,7 +816,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             if (hi < 0) { hi = Nx - 1; ok = (p.bc_lo[0] == BC_BLOCH); }
             if (ok) {
                 hcomp = (q < TY) ? 1 : 2;  // x-halo column of slot 1 and slot 2
-                if (MODE == CURL3_DIVG && hcomp == 2) hcomp = -1;  // divergence: only slot 1 (F_x) is x-differenced
+                if (DIVLIKE && hcomp == 2) hcomp = -1;  // divergence: only slot 1 (F_x) is x-differenced
                 if (MODE == CURL3_GRAD) hcomp = (q < TY) ? 0 : -1;  // gradient: the x-halo of slot 0 (f)
                 hdst = (y + (fy ? 0 : 1)) * PITCH + (fx ? nvx : 0);
                 hsrc = (int64_t)(j0 + y) * sy + hi;
@@ -777,8 +826,16 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
     const T *const hbase = (hcomp >= 0) ? p.F[hcomp] + hsrc : nullptr;
     T *const hsm = sm + (hcomp >= 0 ? hcomp * COMP + hdst : 0);
 
-    const C cxi = valid ? p.c[0][i] : C{};
-    const C cyj = valid ? p.c[1][j] : C{};
+    // (arithmetic means carry no coefficient tables)
+    const bool has_cx = (MODE != CURL3_MEAN) || p.m[0].weighted, has_cy = (MODE != CURL3_MEAN) || p.m[1].weighted;
+    const C cxi = (valid && has_cx) ? p.c[0][i] : C{};
+    const C cyj = (valid && has_cy) ? p.c[1][j] : C{};
+    // weighted means of an interior cell: ∆x[i], ∆x[i±1], ∆y[j], ∆y[j±1]
+    C mwx = C{}, mwxn = C{}, mwy = C{}, mwyn = C{};
+    if (MODE == CURL3_MEAN && valid) {
+        if (p.m[0].weighted) { mwx = p.m[0].w[i]; mwxn = p.m[0].w[min(max(i + (fx ? 1 : -1), 0), Nx - 1)]; }
+        if (p.m[1].weighted) { mwy = p.m[1].w[j]; mwyn = p.m[1].w[min(max(j + (fy ? 1 : -1), 0), Ny - 1)]; }
+    }
     // backward difference c·(cur − nb) == (−c)·(nb − cur) exactly: fold the direction into the sign
     const C cxs = fx ? cxi : neg(cxi);
     const C cys = fy ? cyj : neg(cyj);
@@ -817,7 +874,7 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
             if (kp >= 0 && kp < Nz) {
                 if (valid) {
                     cp_async_elem(st + self, p.F[0] + off_issue + ij);
-                    if (MODE == CURL3_CURL || (MODE == CURL3_DIVG && centre)) cp_async_elem(st + COMP + self, p.F[1] + off_issue + ij);
+                    if (MODE == CURL3_CURL || (DIVLIKE && centre)) cp_async_elem(st + COMP + self, p.F[1] + off_issue + ij);
                     if (MODE != CURL3_GRAD && centre) cp_async_elem(st + 2 * COMP + self, p.F[2] + off_issue + ij);
                 }
                 if (centre && hcomp >= 0) cp_async_elem(hsm + stage_issue * STAGE, hbase + off_issue);
@@ -858,12 +915,31 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
         const T xhi = shi[self], yhi = shi[COMP + self];
         const T xc = fz ? xlo : xhi;
         // slot 1 is staged on centre planes only for the divergence: read it there, not through the carry
-        const T yc = (MODE == CURL3_GRAD) ? Z : ((MODE == CURL3_DIVG) ? sc[COMP + self] : (fz ? ylo : yhi));
+        const T yc = (MODE == CURL3_GRAD) ? Z : (DIVLIKE ? sc[COMP + self] : (fz ? ylo : yhi));
         const T zc = (MODE == CURL3_GRAD) ? Z : sc[2 * COMP + self];
         const C czk = p.c[2][k];
         T gx, gy, gz;
 
-        if (tile_plain && k > 0 && k < Nz - 1) {
+        if constexpr (MODE == CURL3_MEAN) {
+            // slot 0 = F_z averaged along z (register carry), slot 1 = F_x along x, slot 2 = F_y along y
+            const T zcur = fz ? xlo : xhi, znb = fz ? xhi : xlo;
+            const T xnbv = sc[COMP + xnb], ynbv = sc[2 * COMP + ynb];
+            T r0, r1, r2;
+            if (tile_plain && k > 0 && k < Nz - 1) {
+                const bool wz = p.m[2].weighted != 0;
+                const C mcz = wz ? p.c[2][k] : C{}, mwz = wz ? p.m[2].w[k] : C{}, mwzn = wz ? p.m[2].w[fz ? k + 1 : k - 1] : C{};
+                r0 = mean_plain<T, C>(wz, p.m[2].a2, mcz, mwz, mwzn, zcur, znb);
+                r1 = mean_plain<T, C>(p.m[0].weighted != 0, p.m[0].a2, cxi, mwx, mwxn, yc, xnbv);
+                r2 = mean_plain<T, C>(p.m[1].weighted != 0, p.m[1].a2, cyj, mwy, mwyn, zc, ynbv);
+            } else {
+                r0 = mean_eval<T, C>(p, 2, k, Nz, zcur, znb);
+                r1 = mean_eval<T, C>(p, 0, valid ? i : 0, Nx, yc, xnbv);
+                r2 = mean_eval<T, C>(p, 1, valid ? j : 0, Ny, zc, ynbv);
+            }
+            gx = ADD ? add(g0, r0) : r0;
+            gy = ADD ? add(g1, r1) : r1;
+            gz = ADD ? add(g2, r2) : r2;
+        } else if (tile_plain && k > 0 && k < Nz - 1) {
             // ---- fast path: no boundary in reach; every term is c·(nb − cur) ------------------------
             if (MODE == CURL3_CURL) {
                 const T xn = sc[ynb], zn = sc[2 * COMP + ynb];

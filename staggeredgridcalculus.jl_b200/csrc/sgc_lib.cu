@@ -365,6 +365,10 @@ extern "C" int sgc_op_create_mean(sgc_op **op_out, int dtype, int ndim, const in
         OP_TRY(add_term(op, b, dl ? KIND_MEAN_WEIGHTED : KIND_MEAN_ARITH, d, d, d, isfwd[d], dl ? dl[d] : nullptr,
                         dlpinv ? dlpinv[d] : nullptr, coef_complex, isbloch[d], e ? e + 2 * d : nullptr,
                         alpha_of(alpha), 1));
+    if (ndim == 3) {  // one launch when the three terms share the coefficient type
+        op->fused_mean = true;
+        for (const Term &t : op->terms) op->fused_mean = op->fused_mean && (t.cc == op->terms[0].cc);
+    }
     OP_EPILOGUE();
 }
 
@@ -692,6 +696,15 @@ static int apply_typed(const sgc_op *op, T *G, const T *F, int opmode, const voi
         }
         if (s || done) return s;
     }
+    // apply_mean! on a 3-D grid: one launch (variant 2 / 3: the reference's three sweeps); slabs keep the sweeps
+    if (op->fused_mean && (op->variant & 0xF) != 2 && (op->variant & 0xF) != 3 && !ghost && !op->lo_iface && !op->hi_iface && !op->has_slab_w) {
+        if constexpr (std::is_same<T, double>::value) {
+            return sgc_launch_mean3<double, double>(op, G, F, user_add, k_begin, k_end, st);
+        } else {
+            return op->terms[0].cc ? sgc_launch_mean3<cplx, cplx>(op, G, F, user_add, k_begin, k_end, st)
+                                   : sgc_launch_mean3<cplx, double>(op, G, F, user_add, k_begin, k_end, st);
+        }
+    }
     // per-block sweeps in the reference's order; the first executed step of each output
     // component uses the caller's OP, the following ones `+=`.
     int cur_out = -1;
@@ -746,6 +759,7 @@ extern "C" int sgc_op_launches(const sgc_op *op, int opmode) {
     if (op->fused_pat >= 0 && (op->variant & 0xF) != 2 && (op->variant & 0xF) != 3 &&
         op->N[0] % (op->dtype == SGC_C128 ? 1 : 2) == 0 && (op->M * (op->dtype == SGC_C128 ? 16 : 8)) % 16 == 0)
         return 1;  // (aligned, full-range calls; others fall back to the sweeps)
+    if (op->fused_mean && (op->variant & 0xF) != 2 && (op->variant & 0xF) != 3 && !op->lo_iface && !op->hi_iface && !op->has_slab_w) return 1;
     int n = 0, cur_out = -1;
     bool add_mode = opmode == SGC_OP_ADD;
     for (const Term &t : op->terms) {
