@@ -143,7 +143,13 @@ int sgc_op_set_slab_weights(sgc_op *op, const double *dw_below, const double *dw
  * register-prefetch z-march, 2 = unfused per-block sweeps, the reference's own structure;
  * for single-block operators 3 = force the scalar k_term kernel instead of the vectorised ones);
  * bits 4-7 give the number of ring stages for kernel 0 (0 = default 4), bits 8-11 the
- * CTAs-per-SM register target it was compiled for (0 = default). */
+ * CTAs-per-SM register target it was compiled for (0 = default).  apply_mean! on a 3-D grid: 0 = one launch of
+ * the staged z-march, 2 / 3 = the three sweeps.
+ * On the SECOND operator of sgc_op_apply_curlcurl the low 4 bits select the fused curl-of-curl kernel: 0 = default
+ * (k_cc6 — TMA-fed, two z-planes per barrier interval — where it applies: ComplexF64, all-symmetric box, forward then
+ * backward in z, no slab ghosts; otherwise the third generation), 2 = third generation (warp roles, cp.async ring),
+ * 1 = first generation, 4 / 5 = the TMA experiments k_cc4 / k_cc5, 6 = k_cc6 or, where it does not apply, the third
+ * generation; bits 4-7 = ring stages (k_cc6: pairs of planes). */
 int sgc_op_set_tuning(sgc_op *op, int tile_x, int tile_y, int march_z, int variant);
 
 /* G OP α·(operator)(F).  Returns immediately; work is queued on `stream`. */
