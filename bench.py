@@ -326,7 +326,14 @@ class Leg:
         # W steps are a floor, not a duration: after the oracle comparison (seconds of CPU work, idle GPUs and NVLink
         # links) a few milliseconds of stepping do not bring clocks and links back up — keep stepping for ~0.2 s
         per_step = max((time.perf_counter() - t_w) / max(warmup, 1), 1e-5)
-        for _ in range(min(2000, int(0.2 / per_step))):
+        n_more = min(2000, int(0.2 / per_step))
+        if self.world > 1:
+            # every rank MUST run the same number of synchronised applies (a rank that runs one more spins in its
+            # boundary CTAs for a neighbour that never comes): agree on the largest count
+            cnt = torch.tensor([n_more], device="cuda", dtype=torch.int64)
+            dist.all_reduce(cnt, op=dist.ReduceOp.MAX)
+            n_more = int(cnt.item())
+        for _ in range(n_more):
             self.step()
         self.barrier()
         graph, launches_per_step, run_step = None, None, self.step
@@ -491,7 +498,9 @@ def main():
     numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None  # pinned buffers on the GPU's own node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # (a hung collective should end the run in minutes, not after NCCL's default 10)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=240))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
     leg = Leg(S, torch, dist, NLOCAL, rank, world, args)
@@ -507,6 +516,9 @@ def main():
 
     use_graph = args.graph == "on" or (args.graph == "auto" and world > 1 and arena is not None and leg.sync == "flags")
     tm = leg.time(args.steps, args.warmup, use_graph, local_rank)
+    if leg.arena is not None and leg.arena.timeouts() != 0:  # a device-side wait on a neighbour gave up: the numbers mean nothing
+        print(f"rank {rank}: {leg.arena.timeouts()} neighbour waits timed out inside the synchronised applies", file=sys.stderr)
+        sys.exit(3)
     ms_step, value = tm["ms_step"], tm["value"]
 
     # ---- end-to-end: pinned host arrays → H2D → two curls → D2H, every step ----------------------

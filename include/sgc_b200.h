@@ -239,6 +239,11 @@ int sgc_peer_free(sgc_comm *comm, void *dptr);
 int sgc_peer_barrier(sgc_comm *comm, void *stream);
 /* Synchronised applies finished by this rank so far (reads the control block; synchronises `stream`). */
 int sgc_comm_epoch(sgc_comm *comm, int64_t *epoch, void *stream);
+/* Device-side waits on a neighbour (barrier kernel, synchronised applies) are bounded: a waiter that polled for
+ * seconds without seeing its neighbour counts a timeout in the control block and goes on, so that ranks issuing
+ * different numbers of synchronised calls (or a rank that died) cannot hang the GPU.  0 in a correct run; anything
+ * else means the results since the last check are not valid.  Reads the control block; synchronises `stream`. */
+int sgc_comm_timeouts(sgc_comm *comm, int64_t *count, void *stream);
 
 /* Neighbour synchronisation folded into the fused 3-D curl kernel — no barrier kernel between applies.
  * sgc_op_attach_comm names the ranks that own the slab below / above this one (-1: none; for a Bloch z

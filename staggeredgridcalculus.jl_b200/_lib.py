@@ -104,6 +104,7 @@ _PROTOS = {
     "sgc_peer_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgc_peer_barrier": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sgc_comm_epoch": (C.c_int, [C.c_void_p, i64p, C.c_void_p]),
+    "sgc_comm_timeouts": (C.c_int, [C.c_void_p, i64p, C.c_void_p]),
     "sgc_op_attach_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "sgc_op_apply_synced": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, vpp, C.c_void_p]),
     "sgc_op_apply_curlcurl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),

@@ -43,7 +43,7 @@ __global__ void k_peer_barrier(long long *ctrl, long long *const *peer_ctrl, int
     __threadfence_system();
     if (j < world && j != rank) {
         st_release_sys(peer_ctrl[j] + SGC_CTRL_BAR_SLOTS + rank, n);
-        while (ld_acquire_sys(ctrl + SGC_CTRL_BAR_SLOTS + j) < n) __nanosleep(32);
+        wait_flag_sys(ctrl + SGC_CTRL_BAR_SLOTS + j, n, ctrl, 32);
     }
     __syncthreads();
     if (j == 0) {
@@ -225,6 +225,16 @@ extern "C" int sgc_comm_epoch(sgc_comm *c, int64_t *epoch, void *stream) {
     CUDA_TRY(cudaMemcpyAsync(&v, c->ctrl + SGC_CTRL_EPOCH, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     *epoch = v;
+    return SGC_OK;
+}
+
+// Waits on a neighbour that gave up after SGC_SPIN_LIMIT polls (0 in a correct run; host read-back, synchronises).
+extern "C" int sgc_comm_timeouts(sgc_comm *c, int64_t *count, void *stream) {
+    REQUIRE(c && count, "NULL argument");
+    long long v = 0;
+    CUDA_TRY(cudaMemcpyAsync(&v, c->ctrl + SGC_CTRL_TIMEOUTS, sizeof v, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    *count = v;
     return SGC_OK;
 }
 

@@ -368,7 +368,10 @@ __global__ void __launch_bounds__(256) k_fill_zero(T *G, int64_t n) {
 // ---------------------------------------------------------------------------------------------
 // slots of a rank's control block (int64 each; sgc_comm.cu allocates and peer-maps it)
 enum : int { SGC_CTRL_FLAG_LO = 0, SGC_CTRL_FLAG_HI = 1, SGC_CTRL_EPOCH = 2, SGC_CTRL_TICKETS = 3 /* 2 x uint32 */,
-             SGC_CTRL_SIDES_DONE = 4 /* uint32 */, SGC_CTRL_BAR_COUNT = 5, SGC_CTRL_BAR_SLOTS = 8 /* + world */ };
+             SGC_CTRL_SIDES_DONE = 4 /* uint32 */, SGC_CTRL_BAR_COUNT = 5, SGC_CTRL_TIMEOUTS = 6, SGC_CTRL_BAR_SLOTS = 8 /* + world */ };
+// a neighbour that never arrives (ranks issuing different numbers of synchronised applies, a rank that died) must not
+// hang the GPU: after this many polls (seconds) the waiter counts a timeout in its control block and goes on
+constexpr unsigned SGC_SPIN_LIMIT = 1u << 23;
 
 // apply_mean! through the staged z-march (k_curl3p MODE = CURL3_MEAN): the m̂ coefficients of one axis
 // (the fields of TermParams, matrixfree/mean.jl:102-922)
@@ -458,6 +461,17 @@ SGC_D long long ld_volatile_s64(const long long *p) {
 }
 SGC_D void st_volatile_s64(long long *p, long long v) {
     asm volatile("st.volatile.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until *flag >= want (written by a peer over NVLink); bounded, see SGC_SPIN_LIMIT
+SGC_D void wait_flag_sys(const long long *flag, long long want, long long *ctrl, unsigned ns) {
+    unsigned polls = 0;
+    while (ld_acquire_sys(flag) < want) {
+        __nanosleep(ns);
+        if (++polls > SGC_SPIN_LIMIT) {
+            atomicAdd(reinterpret_cast<unsigned long long *>(ctrl + SGC_CTRL_TIMEOUTS), 1ull);
+            break;
+        }
+    }
 }
 
 // One CTA owns a TX×TY column of cells and marches `march` planes up in z.
@@ -855,9 +869,9 @@ __global__ void __launch_bounds__(TX *TY, MINB) k_curl3p(const __grid_constant__
         if (lin == 0) {
             const long long done = ld_volatile_s64(p.sync_ctrl + SGC_CTRL_EPOCH);  // my finished applies
             if (k0 == 0 && p.sync_side[0])
-                while (ld_acquire_sys(p.sync_ctrl + SGC_CTRL_FLAG_LO) < done) __nanosleep(64);
+                wait_flag_sys(p.sync_ctrl + SGC_CTRL_FLAG_LO, done, p.sync_ctrl, 64);
             if (k1 == Nz && p.sync_side[1])
-                while (ld_acquire_sys(p.sync_ctrl + SGC_CTRL_FLAG_HI) < done) __nanosleep(64);
+                wait_flag_sys(p.sync_ctrl + SGC_CTRL_FLAG_HI, done, p.sync_ctrl, 64);
         }
         __syncthreads();
     }

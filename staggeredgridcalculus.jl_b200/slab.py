@@ -242,6 +242,13 @@ class PeerArena:
         check(lib.sgc_comm_epoch(self.comm, C.byref(v), stream_handle(None)))
         return int(v.value)
 
+    def timeouts(self) -> int:
+        """Device-side waits on a neighbour that gave up (`sgc_comm_timeouts`): 0 in a correct run."""
+        from .device import stream_handle
+        v = C.c_int64()
+        check(lib.sgc_comm_timeouts(self.comm, C.byref(v), stream_handle(None)))
+        return int(v.value)
+
     def assert_same(self, value, what="slab shape"):
         """The peer paths address the neighbour's planes with the LOCAL slab extents: all ranks must agree."""
         vals = [None] * self.world

@@ -128,6 +128,7 @@ def _worker_flags(rank, world, port, results):
                 c2.apply(A, B, "=")
             torch.cuda.synchronize()
             ok = ok and np.array_equal(A.numpy(), ref)
+        ok = ok and arena.timeouts() == 0  # no device-side wait on a neighbour gave up
         results[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
