@@ -97,20 +97,29 @@ class ClockSampler(threading.Thread):
                  nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
         while not self.stop_flag:
             try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
                 r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
+                self.samples.append((time.perf_counter(), mhz, r))
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
+        self.names = names
 
-    def result(self):
+    def result(self, t0=None, t1=None):
+        """Median SM clock and the throttle reasons seen between the host times t0 and t1 (the timed region; the thread
+        is started before the barriers in front of it so that its set-up cost is not inside it)."""
         self.stop_flag = True
-        if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
-        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        self.join(timeout=1.0)
+        inside = [q for q in self.samples if (t0 is None or q[0] >= t0) and (t1 is None or q[0] <= t1)] or self.samples
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        reasons = set()
+        for _, _, r in inside:
+            for bit, name in getattr(self, "names", {}).items():
+                if r & bit:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median([q[1] for q in inside])), "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(inside)}
 
 
 def cpu_reference_rate(dlinv_prim, dlinv_dual, nz, target_seconds, threads=None):
@@ -362,24 +371,29 @@ class Leg:
                 run_step = graph.replay
                 for _ in range(max(2, warmup)):
                     run_step()
+        # the clock sampler (NVML initialisation: milliseconds, different on every rank) starts BEFORE the barriers: nothing
+        # but the event record sits between the device-side barrier and the first step, so no rank starts its timed
+        # region late and makes its neighbours' boundary CTAs wait inside theirs
+        launches0 = S.launch_count()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         self.barrier()
         if self.arena is not None:
             # the host barrier releases the ranks up to a millisecond apart; a device-side barrier in front of the
             # first event lines the GPUs up, so that no rank's timed region starts with a wait for a late neighbour
             self.arena.barrier()
-        launches0 = S.launch_count()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
         t_host0 = time.perf_counter()
         for _ in range(steps):
             run_step()
         host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps
         ev1.record()
+        ev1.synchronize()
+        t_host1 = time.perf_counter()
         self.barrier()
         ms_mine = ev0.elapsed_time(ev1) / steps
-        clocks = sampler.result()
+        clocks = sampler.result(t_host0, t_host1)
         launches = (launches_per_step * steps) if graph is not None else (S.launch_count() - launches0)
         per_rank = [ms_mine]
         if self.world > 1:
