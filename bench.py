@@ -957,13 +957,30 @@ def bench_other_configs(S, torch, peak, c_dual, c_prim, E, E2, ms_two_curls):
                  ("create_mean", lambda: S.create_mean([True, False, True], da, da, [True, True, False])),
                  ("create_divg", lambda: S.create_divg([True] * 3, da, [True, True, False])),
                  ("create_grad", lambda: S.create_grad([False] * 3, da, [True, True, False])))
+        import ctypes as C
+        from sgc_b200 import matrix as MX
+        from sgc_b200._lib import lib as _lib_, check as _check_
+        from sgc_b200.device import stream_handle as _sh_
         for name, fn in cases:
             A = fn()
             nnz, ncol = A.nnz, A.n
-            del A
-            ms = _time(torch, fn, iters=5, warm=1)
+            ms = _time(torch, fn, iters=5, warm=1)  # the whole reference-shaped call: tables, handle, output allocation, kernel
             alg = nnz * 16 + (ncol + 1) * 8
-            asm[name] = {"ms": r4(ms), "gnnz_per_s": r4(nnz / ms / 1e6), "frac": r4(alg / ms / 1e6 / peak)}
+            # the device work alone: one fill pass (colptr + rowval + nzval) on a held handle into the same arrays
+            finish = MX._finish
+            try:
+                MX._finish = lambda a, *args, **kw: a
+                hnd = fn()
+            finally:
+                MX._finish = finish
+            st, nn = _sh_(None), C.c_int64()
+            _check_(_lib_.sgc_asm_count(hnd.h, C.byref(nn), st))
+            fill = lambda: _check_(_lib_.sgc_asm_fill_all(hnd.h, C.c_void_p(A.colptr.data_ptr()), 1, C.c_void_p(A.rowval.data_ptr()),
+                                                          C.c_void_p(A.nzval.data_ptr()), st))
+            ms_fill = _time(torch, fill, iters=10, warm=2)
+            asm[name] = {"ms_whole_call": r4(ms), "ms_fill": r4(ms_fill), "gnnz_per_s": r4(nnz / ms_fill / 1e6), "frac": r4(alg / ms_fill / 1e6 / peak),
+                         "frac_whole_call": r4(alg / ms / 1e6 / peak)}
+            del A, hnd
         res["assembly_others_384_f64"] = asm
         # call latency of the reference-shaped one-shot entry point (handle cached inside the library) against a held
         # handle, on a 64³ grid where the kernel itself takes ~10 µs (BASELINE configs[0] size)

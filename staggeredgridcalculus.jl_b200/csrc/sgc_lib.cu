@@ -558,13 +558,13 @@ static void launch_fused_one(const FusedParams<T, C> &p, cudaStream_t st) {
 #ifdef SGC_FUSED_SWEEP
 // development sweep (tools/sweep_fused.py): vector width × rows per thread × CTAs/SM × split launch,
 // Float64 non-accumulating TE / TM / divg-3D / grad-3D only
-template <typename T, typename C, int P>
+template <typename T, typename C, int P, bool ADD>
 static bool launch_fused_sweep(const FusedParams<T, C> &p, int vecbytes, int rows, int minb, int split, cudaStream_t st) {
     (void)split;
     if constexpr (std::is_same<T, double>::value || std::is_same<C, cplx>::value) {
 #define SW(VB, RR, MB)                                                                                      \
         if (vecbytes == VB && rows == RR && minb == MB) {                                                   \
-            launch_fused_one<T, C, P, false, VB / (int)sizeof(T), RR, MB, FUSED_ALL>(p, st);                 \
+            launch_fused_one<T, C, P, ADD, VB / (int)sizeof(T), RR, MB, FUSED_ALL>(p, st);                   \
             return true; }
         SW(32, 4, 1) SW(32, 4, 2) SW(32, 2, 2) SW(32, 2, 3) SW(32, 2, 4) SW(16, 4, 2) SW(16, 4, 3) SW(16, 4, 4) SW(16, 2, 3) SW(16, 2, 4)
         SW(32, 1, 3) SW(32, 1, 4) SW(16, 1, 4)
@@ -590,6 +590,11 @@ static void launch_fused_pat(const FusedParams<T, C> &p, bool add_mode, cudaStre
         launch_fused_cfg<T, C, P, 16, 4, 2>(p, add_mode, st);
     } else if constexpr (P == PAT_GATHER_XY || P == PAT_GATHER_YX) {
         if (p.Nx % 4 == 0) launch_fused_cfg<T, C, P, 32, 1, 4>(p, add_mode, st);
+        else launch_fused_cfg<T, C, P, 16, 4, 3>(p, add_mode, st);
+    } else if constexpr (P == PAT_ONE_Y) {
+        // accumulating ∂y (read F, read-modify-write G: 24 B/cell): 32-byte vectors of 2 rows, 4 CTAs/SM — 8192² Float64
+        // 0.311 → 0.249 ms (profiles/r2_sweep_fused_y.jsonl); the non-accumulating form keeps 16-byte vectors of 4 rows
+        if (add_mode && p.Nx % 4 == 0) launch_fused_one<T, C, P, true, 32 / (int)sizeof(T), 2, 4>(p, st);
         else launch_fused_cfg<T, C, P, 16, 4, 3>(p, add_mode, st);
     } else {
         launch_fused_cfg<T, C, P, 16, 4, 3>(p, add_mode, st);
@@ -643,13 +648,15 @@ static int launch_fused(const sgc_op *op, T *G, const T *F, const void *const *g
     // (profiles/r1_sweep_fused.jsonl): 16-byte vectors and 3-4 resident CTAs win almost everywhere;
     // the Float64 two-input compositions prefer 32-byte vectors of a single row.
 #ifdef SGC_FUSED_SWEEP
-    if (op->tile_x && !add_mode) {
+    if (op->tile_x && (!add_mode || op->fused_pat == 7)) {
         bool ok = false;
         switch (op->fused_pat) {
-            case 1: ok = launch_fused_sweep<T, C, 1>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
-            case 2: ok = launch_fused_sweep<T, C, 2>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
-            case 4: ok = launch_fused_sweep<T, C, 4>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
-            case 5: ok = launch_fused_sweep<T, C, 5>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 1: ok = launch_fused_sweep<T, C, 1, false>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 2: ok = launch_fused_sweep<T, C, 2, false>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 4: ok = launch_fused_sweep<T, C, 4, false>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 5: ok = launch_fused_sweep<T, C, 5, false>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
+            case 7: ok = add_mode ? launch_fused_sweep<T, C, 7, true>(p, op->tile_x, op->tile_y, op->march, 0, st)
+                                  : launch_fused_sweep<T, C, 7, false>(p, op->tile_x, op->tile_y, op->march, 0, st); break;
             default: break;
         }
         if (!ok) return fail(SGC_ERR_INVALID, "fused sweep: configuration not built");

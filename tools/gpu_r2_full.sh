@@ -18,3 +18,19 @@ try:
 except Exception as ex:
     print('parse failed', ex)
 PY
+# ncu launch list of the timed step (same command as the round-1 list): the step is two launches of k_curl3p
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_bench_launches.csv \
+    python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --no-assembly --no-extras --no-cfg5 > gpurun_out/r2_ncu_bench.log 2>&1; echo "ncu rc=$?"
+python - <<'PY'
+import csv, collections
+rows = list(csv.reader(l for l in open('gpurun_out/r2_bench_launches.csv') if not l.startswith('==')))
+hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+tot = collections.Counter(); cnt = collections.Counter()
+for r in rows[1:]:
+    if len(r) < len(hdr): continue
+    try: v = float(r[ix['Metric Value']].replace(',', ''))
+    except Exception: continue
+    k = r[ix['Kernel Name']][:70]; tot[k] += v; cnt[k] += 1
+s = sum(tot.values())
+for k, v in tot.most_common(6): print(f"{100*v/s:5.1f}%  n={cnt[k]:4d}  avg={v/cnt[k]/1e3:8.1f} us  {k}")
+PY
