@@ -393,7 +393,8 @@ int sgc_asm_fill_all(sgc_asm *a, int64_t *colptr, int index_base, int64_t *rowva
 /* Test switches (the tests run every path and require identical output).  force_count_pass bit 0: use the count
  * kernel + device scan even where the closed form applies; bit 1: interior cells take the general entry path
  * (block walk + sort) instead of the host-sorted descriptors; bit 2: the CTA-granular fill kernel (block scan) instead
- * of the warp-granular one where the closed form applies. */
+ * of the warp-granular one where the closed form applies; bit 3: one column per thread where the warp-granular kernel
+ * would give a thread several consecutive cells. */
 int sgc_asm_set_tuning(sgc_asm *a, int force_count_pass);
 
 /* Two-step form with a separate colptr pass (kept for callers that want the structure first).

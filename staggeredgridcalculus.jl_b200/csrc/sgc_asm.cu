@@ -359,6 +359,7 @@ extern "C" int sgc_asm_set_tuning(sgc_asm *a, int force_count_pass) {
     a->force_count_pass = (force_count_pass & 1) != 0;
     a->no_fast = (force_count_pass & 2) != 0;
     a->no_warp = (force_count_pass & 4) != 0;
+    a->no_cells = (force_count_pass & 8) != 0;
     a->nnz = -1;
     a->counted = false;
     return SGC_OK;
@@ -475,8 +476,21 @@ static int asm_launch(const sgc_asm *a, int index_base, const int64_t *colptr_in
     if (a->ncta == 0) return SGC_OK;
     if (MODE == ASM_FILL_ALL && p.prefix_enabled && !a->no_warp) {
         // closed-form offsets: warp-granular kernel (no CTA-wide barrier, no block scan)
+        if constexpr (NCOLS == 1) {
+            // one column per group (block ordering, create_∂, create_m̂, create_grad): a thread takes CPT consecutive cells of
+            // the row so that the offset arithmetic is shared by CPT·E entries (whole matrix only, Nx a multiple of CPT)
+            constexpr int CPT = (E == 2) ? 4 : 2;
+            if (a->col_end < 0 && a->N[0] % CPT == 0 && !a->no_cells) {
+                const size_t smem = (sizeof(T) + sizeof(R)) * (size_t)ASM_BLOCK * (CPT * E + 1);
+                auto kern = k_asm_warp<T, IDX, R, ASM_BLOCK, CPT, E, true>;
+                if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                const int64_t nthreads = p.ngroups / CPT;
+                kern<<<(unsigned)((nthreads + ASM_BLOCK - 1) / ASM_BLOCK), ASM_BLOCK, smem, st>>>(p, colptr_out, rowval, nzval);
+                return check_launch("k_asm_warp<cells>");
+            }
+        }
         const size_t smem = (sizeof(T) + sizeof(R)) * (size_t)ASM_BLOCK * (NCOLS * E + 1);
-        auto kern = k_asm_warp<T, IDX, R, ASM_BLOCK, NCOLS, E>;
+        auto kern = k_asm_warp<T, IDX, R, ASM_BLOCK, NCOLS, E, false>;
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)a->ncta, ASM_BLOCK, smem, st>>>(p, colptr_out, rowval, nzval);
         return check_launch("k_asm_warp");

@@ -491,64 +491,79 @@ __global__ void __launch_bounds__(BLOCK) k_asm_group(const __grid_constant__ Asm
 // columns are all full (`__all_sync`) writes an arithmetic colptr and emits interior cells from the host-sorted
 // descriptors; any other warp runs the general entry path behind an intra-warp shuffle scan.
 // ---------------------------------------------------------------------------------------------
-template <typename T, typename IDX, typename R, int BLOCK, int NCOLS, int E>
+// CELLS = false: a thread owns the NCOLS = Kin columns of one grid cell (component-major ordering).
+// CELLS = true : a thread owns NCOLS consecutive columns of ONE block column (block ordering, or a single-column operator:
+//                create_∂, create_m̂, create_grad) — consecutive cells along x, Nx a multiple of NCOLS so that they never leave
+//                the row; the per-warp offset arithmetic and the per-thread subscript divisions are then shared by
+//                NCOLS·E entries instead of E (create_∂ 384³: 0.75 → see profiles/r2_time_asm_cells.jsonl).
+template <typename T, typename IDX, typename R, int BLOCK, int NCOLS, int E, bool CELLS>
 __global__ void __launch_bounds__(BLOCK) k_asm_warp(const __grid_constant__ AsmParams<T> p, int64_t *__restrict__ colptr_out,
                                                     int64_t *__restrict__ rowval, T *__restrict__ nzval) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int PADK = NCOLS * E;
     constexpr int WSLOTS = 32 * (PADK + 1);
     constexpr int NWARP = BLOCK / 32;
+    constexpr int CPG = CELLS ? NCOLS : 1;  // matrix columns per group index of AsmParams (CELLS: a group there is ONE column)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     T *s_vals = reinterpret_cast<T *>(smem_raw) + wid * WSLOTS;
     R *s_rows = reinterpret_cast<R *>(smem_raw + sizeof(T) * (size_t)WSLOTS * NWARP) + wid * WSLOTS;
-    const int64_t g0 = ((int64_t)blockIdx.x + p.cta_first) * BLOCK + wid * 32;  // the warp's first group
-    if (g0 >= p.g_end) return;
-    const int64_t g = g0 + lane;
-    const bool live = g < p.g_end;
+    // thread index in units of NCOLS columns; g_end of the parameters counts groups of cols_per_group columns
+    const int64_t t_end = CELLS ? p.g_end / NCOLS : p.g_end;
+    const int64_t t0 = (CELLS ? (int64_t)blockIdx.x : (int64_t)blockIdx.x + p.cta_first) * BLOCK + wid * 32;  // the warp's first thread index
+    if (t0 >= t_end) return;
+    const int64_t t = t0 + lane;
+    const bool live = t < t_end;
     int nu0 = 0;
     IDX c = 0, sub[3] = {0, 0, 0};
-    if (live) group_decode<T, IDX>(p, g, nu0, c, sub);
+    if (live) group_decode<T, IDX>(p, t * CPG, nu0, c, sub);
     int cnt[NCOLS];
     int mine = 0;
 #pragma unroll
     for (int q = 0; q < NCOLS; ++q) {
-        cnt[q] = live ? p.cnt_tab[nu0 + q][0][sub[0]] + p.cnt_tab[nu0 + q][1][sub[1]] + p.cnt_tab[nu0 + q][2][sub[2]] : 0;
+        if (CELLS) cnt[q] = live ? p.cnt_tab[nu0][0][sub[0] + q] + p.cnt_tab[nu0][1][sub[1]] + p.cnt_tab[nu0][2][sub[2]] : 0;
+        else cnt[q] = live ? p.cnt_tab[nu0 + q][0][sub[0]] + p.cnt_tab[nu0 + q][1][sub[1]] + p.cnt_tab[nu0 + q][2][sub[2]] : 0;
         mine += cnt[q];
     }
     const int64_t ib = p.index_base;
-    const int64_t base = prefix_entries_before<T, IDX>(p, g0) - p.entry_base;
-    const int64_t col0 = g0 * NCOLS - p.col_base;
-    const int64_t ncol_out = p.g_end * NCOLS - p.col_base;
+    const int64_t base = prefix_entries_before<T, IDX>(p, t0 * CPG) - p.entry_base;
+    const int64_t col0 = t0 * NCOLS - p.col_base;
+    const int64_t ncol_out = t_end * NCOLS - p.col_base;
+    // column q of this thread: block column, cell and subscripts
+    auto col_of = [&](int q, int &nu, IDX &cc, IDX (&ss)[3]) {
+        nu = CELLS ? nu0 : nu0 + q;
+        cc = CELLS ? c + (IDX)q : c;
+        ss[0] = CELLS ? sub[0] + (IDX)q : sub[0]; ss[1] = sub[1]; ss[2] = sub[2];
+    };
     if (__all_sync(0xffffffffu, mine == PADK)) {
         // ---- every column of the warp holds exactly E entries ----------------------------------------------------
+        // (thread-major staging: thread `lane` owns the slots lane·(PADK+1) …, i.e. the warp's columns lane·NCOLS + q)
 #pragma unroll
         for (int q = 0; q < NCOLS; ++q) {
             const int cc = lane + q * 32;
             colptr_out[col0 + cc] = base + ib + (int64_t)E * cc;
         }
-        if (g == p.g_end - 1) colptr_out[ncol_out] = base + ib + 32 * PADK;
+        if (t == t_end - 1) colptr_out[ncol_out] = base + ib + 32 * PADK;
         const int s0 = lane * (PADK + 1);
-        const bool fast = p.fast_enabled && ((unsigned)sub[0] - p.in_lo[0] <= p.in_span[0]) && ((unsigned)sub[1] - p.in_lo[1] <= p.in_span[1]) &&
-                          ((unsigned)sub[2] - p.in_lo[2] <= p.in_span[2]);
-        if (fast) {
-            const R rowbase = p.cmpfirst ? (R)p.Kout * (R)c : (R)c;
+        const bool in_yz = p.fast_enabled && ((unsigned)sub[1] - p.in_lo[1] <= p.in_span[1]) && ((unsigned)sub[2] - p.in_lo[2] <= p.in_span[2]);
 #pragma unroll
-            for (int q = 0; q < NCOLS; ++q) {
+        for (int q = 0; q < NCOLS; ++q) {
+            int nu;
+            IDX cc, ss[3];
+            col_of(q, nu, cc, ss);
+            if (in_yz && ((unsigned)ss[0] - p.in_lo[0] <= p.in_span[0])) {
+                const R rowbase = p.cmpfirst ? (R)p.Kout * (R)cc : (R)cc;
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
-                    const AsmFastEntry<T> &f = p.fast[nu0 + q][e];
-                    const int64_t at = (int64_t)(f.axis == 0 ? sub[0] : (f.axis == 1 ? sub[1] : sub[2])) + f.dsub;
+                    const AsmFastEntry<T> &f = p.fast[nu][e];
+                    const int64_t at = (int64_t)(f.axis == 0 ? ss[0] : (f.axis == 1 ? ss[1] : ss[2])) + f.dsub;
                     s_rows[s0 + q * E + e] = rowbase + (R)f.rowadd;
                     s_vals[s0 + q * E + e] = f.V[at];
                 }
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < NCOLS; ++q) {
+            } else {
                 R rows[E];
                 T vals[E];
                 int rank[E];
-                column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows, vals, rank);
+                column_entries_of<T, IDX, R, E>(p, nu, cc, ss, rows, vals, rank);
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int slot = s0 + q * E + rank[e];
@@ -585,10 +600,13 @@ __global__ void __launch_bounds__(BLOCK) k_asm_warp(const __grid_constant__ AsmP
         for (int q = 0; q < NCOLS; ++q) {
             colptr_out[col0 + (int64_t)lane * NCOLS + q] = o;
             o += cnt[q];
+            int nu;
+            IDX cc, ss[3];
+            col_of(q, nu, cc, ss);
             R rows[E];
             T vals[E];
             int rank[E];
-            column_entries_of<T, IDX, R, E>(p, nu0 + q, c, sub, rows, vals, rank);
+            column_entries_of<T, IDX, R, E>(p, nu, cc, ss, rows, vals, rank);
 #pragma unroll
             for (int e = 0; e < E; ++e)
                 if (rank[e] < cnt[q]) {  // valid entries rank before the invalid ones
@@ -599,7 +617,7 @@ __global__ void __launch_bounds__(BLOCK) k_asm_warp(const __grid_constant__ AsmP
                 }
             at0 += cnt[q];
         }
-        if (g == p.g_end - 1) colptr_out[ncol_out] = o;  // one-past-the-end entry
+        if (t == t_end - 1) colptr_out[ncol_out] = o;  // one-past-the-end entry
     }
     __syncwarp();
     for (int q = lane; q < total; q += 32) {

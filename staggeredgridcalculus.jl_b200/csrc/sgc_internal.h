@@ -94,6 +94,7 @@ struct sgc_asm {
     int64_t set_total[4] = {0, 0, 0, 0};      // entries of each set when all rows are kept
     bool force_count_pass = false;            // testing: use the count kernel + device scan even when the closed form applies
     bool no_fast = false;                     // testing: interior cells take the general entry path too
+    bool no_cells = false;                    // testing: one column per thread in the warp-granular kernel even where several cells fit
     bool no_warp = false;                     // testing: the CTA-granular kernel (block scan) even where the closed form applies
     // column partition (sgc_asm_set_col_range): the block of columns [col_begin, col_end) as a stand-alone CSC matrix
     int64_t col_begin = 0, col_end = -1;      // -1: all columns

@@ -139,11 +139,13 @@ def _finish(a: _Asm, index_base, row_range, method, device, stream=None) -> Devi
         check(lib.sgc_asm_set_tuning(a.h, 2))
     if method == "cta":  # the CTA-granular fill kernel (block scan) instead of the warp-granular one
         check(lib.sgc_asm_set_tuning(a.h, 4))
+    if method == "onecol":  # the warp-granular kernel with one column per thread (no several-cells-per-thread form)
+        check(lib.sgc_asm_set_tuning(a.h, 8))
     # nnz (closed form, or the count pass for a row partition) so that rowval / nzval can be allocated
     check(lib.sgc_asm_count(a.h, C.byref(nnz), st))
     rowval = torch.empty(nnz.value, dtype=torch.int64, device=dev)
     nzval = torch.empty(nnz.value, dtype=vdt, device=dev)
-    if method in ("direct", "counted", "general", "cta"):  # one pass: colptr + rowval + nzval
+    if method in ("direct", "counted", "general", "cta", "onecol"):  # one pass: colptr + rowval + nzval
         check(lib.sgc_asm_fill_all(a.h, C.c_void_p(colptr.data_ptr()), index_base, C.c_void_p(rowval.data_ptr()),
                                    C.c_void_p(nzval.data_ptr()), st))
     elif method == "twostep":  # colptr first, then rowval / nzval from the given colptr

@@ -130,7 +130,7 @@ def test_create_subcurls_divg_grad_picmp_match_oracle(S):
                                  f"πcmp cmpfirst={cmpfirst} scale={scale} {method}")
 
 
-@pytest.mark.parametrize("N", [(140, 9, 7), (33, 40, 5), (130, 3, 3)])
+@pytest.mark.parametrize("N", [(140, 9, 7), (33, 40, 5), (130, 3, 3), (64, 6, 5)])
 def test_interior_descriptor_path_equals_general_path(S, N):
     """CTAs whose columns are all full emit interior cells from host-sorted descriptors; cells on a grid face and every
     other CTA walk the blocks and sort.  Both must give the same matrix (and the oracle's) for every operator shape."""
@@ -141,23 +141,27 @@ def test_interior_descriptor_path_equals_general_path(S, N):
         for isbloch in ([True] * 3, [True, False, True]):
             for cmpfirst in (True, False):
                 ref = O.create_curl(isfwd, dl, isbloch, e, order_cmpfirst=cmpfirst)
-                for method in ("direct", "general", "cta"):
+                for method in ("direct", "general", "cta", "onecol"):
                     got = S.create_curl(isfwd, dl, isbloch, e, N=N, order_cmpfirst=cmpfirst, method=method)
                     assert_csc_equal(got, ref, f"create_curl N={N} fwd={isfwd} bloch={isbloch} cmpfirst={cmpfirst} {method}")
             for name, mk, mo in (("divg", S.create_divg, O.create_divg), ("grad", S.create_grad, O.create_grad)):
                 for cmpfirst in (True, False):
                     ref = mo(isfwd, dl, isbloch, e, order_cmpfirst=cmpfirst)
-                    for method in ("direct", "general", "cta"):
+                    for method in ("direct", "general", "cta", "onecol"):
                         got = mk(isfwd, dl, isbloch, e, order_cmpfirst=cmpfirst, method=method)
                         assert_csc_equal(got, ref, f"create_{name} N={N} fwd={isfwd} bloch={isbloch} cmpfirst={cmpfirst} {method}")
             ref = O.create_mean(isfwd, dl, dl, isbloch, e)
-            for method in ("direct", "general", "cta"):
+            for method in ("direct", "general", "cta", "onecol"):
                 assert_csc_equal(S.create_mean(isfwd, dl, dl, isbloch, e, method=method), ref, f"create_mean N={N} {method}")
             for nw in (1, 2, 3):
                 ref = O.create_partial(nw, isfwd[nw - 1], N, dl[nw - 1], isbloch[nw - 1], e[nw - 1])
-                for method in ("direct", "general", "cta"):
+                for method in ("direct", "general", "cta", "onecol"):
                     assert_csc_equal(S.create_partial(nw, isfwd[nw - 1], N, dl[nw - 1], isbloch[nw - 1], e[nw - 1], method=method), ref,
                                      f"create_∂ N={N} nw={nw} {method}")
+                ref = O.create_mhat(nw, isfwd[nw - 1], N, dl[nw - 1], dl[nw - 1], isbloch[nw - 1], e[nw - 1])
+                for method in ("direct", "general", "cta", "onecol"):
+                    assert_csc_equal(S.create_mhat(nw, isfwd[nw - 1], N, dl[nw - 1], dl[nw - 1], isbloch[nw - 1], e[nw - 1], method=method), ref,
+                                     f"create_m̂ N={N} nw={nw} {method}")
 
 
 def test_zero_coefficients_are_dropped(S):

@@ -42,7 +42,7 @@ def run(n, cplx, isbloch, cmpfirst=1, tuning=0):
 
 if __name__ == "__main__":
     for n in ([int(a) for a in sys.argv[1:]] or [256, 512]):
-        for tuning in (0, 4, 6):
+        for tuning in (0, 8):
             run(n, False, [1, 1, 1], tuning=tuning)
             run(n, True, [1, 1, 1], tuning=tuning)
             run(n, False, [1, 0, 0], tuning=tuning)
