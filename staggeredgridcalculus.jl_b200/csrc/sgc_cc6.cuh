@@ -8,6 +8,8 @@
 // between two CTA-wide barriers.  Here every thread computes the H points of two consecutive planes, then the output
 // points of two consecutive planes, between one pair of barriers:
 //
+//   * (steady state of boundary-free tiles: ONE straight-line block per iteration, the two output points first — they only
+//     need the H pair of the previous iteration — so that the wait for the arriving E pair sits behind their arithmetic)
 //   * twice the independent arithmetic per thread in one straight-line block (the boundary rules of both points sit
 //     behind ONE branch), half the barriers, loop control, ring bookkeeping and mbarrier waits per cell;
 //   * the plane in the middle of a pair is the upper plane of the first point and the lower plane of the second: its
@@ -75,7 +77,7 @@ SGC_D void curl_point_sym(int flags, C cxs, C cys, bool fx, bool fy, C cz, T xlo
     if (!fx && xedge) { d4 = Z; d5 = Z; }
 }
 
-template <typename C, bool ADD, int TY, int NP, int MINB, bool SP>
+template <typename C, bool ADD, int TY, int NP, int MINB, int SP>
 __global__ void __launch_bounds__(32 * (TY + 1), MINB) k_cc6(const __grid_constant__ CurlCurl4Params<C> P) {
     using T = cplx;
     static_assert(NP >= 3, "the E ring needs at least 3 pairs");
@@ -230,7 +232,78 @@ __global__ void __launch_bounds__(32 * (TY + 1), MINB) k_cc6(const __grid_consta
         // ---- steady state of a boundary-free tile (SP): both phases in ONE straight-line block, the loads of the output
         // points issued between the arithmetic of the H points, so that shared-memory latency and FP64 work overlap
         // inside a warp as well as between warps.  Warp TY (the extra column) keeps the two-phase code below.
-        if (SP && tile_plain && roleD && t >= 2 && t <= Th && k0 + 2 * t - 4 >= 1 && k0 + 2 * t - 1 <= Nz - 2 && 2 * t - 3 < n) {
+        if (SP == 2 && tile_plain && roleD && t >= 2 && t <= Th && k0 + 2 * t - 4 >= 1 && k0 + 2 * t - 1 <= Nz - 2 && 2 * t - 3 < n) {
+            // outputs FIRST: they only need the H pair of the previous iteration, which the barrier has already made
+            // visible, so the wait for the arriving E pair moves behind the arithmetic of the first output point
+            const C czA = lds_at<0>(sC1 + (unsigned)(2 * t) * CS, C{}), czB = lds_at<CS>(sC1 + (unsigned)(2 * t) * CS, C{});
+            const C dzA = lds_at<0>(sC2 + (unsigned)(2 * t - 4) * CS, C{}), dzB = lds_at<CS>(sC2 + (unsigned)(2 * t - 4) * CS, C{});
+            T gA0 = Z, gA1 = Z, gA2 = Z, gB0 = Z, gB1 = Z, gB2 = Z;
+            if (ADD) {
+                gA0 = ldg_plain(p.G[0] + off_out); gA1 = ldg_plain(p.G[1] + off_out); gA2 = ldg_plain(p.G[2] + off_out);
+                gB0 = ldg_plain(p.G[0] + off_out + sz); gB1 = ldg_plain(p.G[1] + off_out + sz); gB2 = ldg_plain(p.G[2] + off_out + sz);
+            }
+            const unsigned out = a_out + h_wr;
+            const unsigned hA = sH + (h_wr ^ (2u * HSTAGE)) + b_q, hB = hA + HSTAGE;
+            const T hxA = lds_at<0>(hA, T{}), hyA = lds_at<HCB>(hA, T{}), hzA = lds_at<2 * HCB>(hA, T{});
+            const T hxynA = lds_at<0>(hA + h_dyb, T{}), hzynA = lds_at<2 * HCB>(hA + h_dyb, T{});
+            const T hyxnA = lds_at<HCB>(hA + h_dxb, T{}), hzxnA = lds_at<2 * HCB>(hA + h_dxb, T{});
+            const T hxB = lds_at<0>(hB, T{}), hyB = lds_at<HCB>(hB, T{}), hzB = lds_at<2 * HCB>(hB, T{});
+            const T hxynB = lds_at<0>(hB + h_dyb, T{}), hzynB = lds_at<2 * HCB>(hB + h_dyb, T{});
+            const T hyxnB = lds_at<HCB>(hB + h_dxb, T{}), hzxnB = lds_at<2 * HCB>(hB + h_dxb, T{});
+            {   // output 2t−4
+                const T a0 = mul(dzA, sub(hxA, bxlo)), a1 = mul(dzA, sub(hyA, bylo));
+                const T a2 = mul(cb.cys, sub(hxynA, hxA)), a3 = mul(cb.cys, sub(hzynA, hzA));
+                const T a4 = mul(cb.cxs, sub(hyxnA, hyA)), a5 = mul(cb.cxs, sub(hzxnA, hzA));
+                stg_stream(p.G[0] + off_out, ADD ? add(add(gA0, neg(a1)), a3) : add(add(Z, neg(a1)), a3));
+                stg_stream(p.G[1] + off_out, ADD ? add(add(gA1, a0), neg(a5)) : add(a0, neg(a5)));
+                stg_stream(p.G[2] + off_out, ADD ? add(add(gA2, neg(a2)), a4) : add(neg(a2), a4));
+            }
+            mbar_wait(bar_efull + 8 * st_cur, e_phase);  // pair P_t has landed
+            const unsigned aA = sE + st_prev * EPAIR + EPLANE + a_q, aB = sE + st_cur * EPAIR + a_q, aC = aB + EPLANE;
+            const T xB = lds_at<0>(aB, T{}), yB = lds_at<ECB>(aB, T{});
+            const T zA = lds_at<2 * ECB>(aA, T{});
+            const T xynA = lds_at<0>(aA + e_dyb, T{}), zynA = lds_at<2 * ECB>(aA + e_dyb, T{});
+            const T yxnA = lds_at<ECB>(aA + e_dxb, T{}), zxnA = lds_at<2 * ECB>(aA + e_dxb, T{});
+            const T xC = lds_at<0>(aC, T{}), yC = lds_at<ECB>(aC, T{});
+            const T zB = lds_at<2 * ECB>(aB, T{});
+            const T xynB = lds_at<0>(aB + e_dyb, T{}), zynB = lds_at<2 * ECB>(aB + e_dyb, T{});
+            const T yxnB = lds_at<ECB>(aB + e_dxb, T{}), zxnB = lds_at<2 * ECB>(aB + e_dxb, T{});
+            {   // output 2t−3
+                const T b0 = mul(dzB, sub(hxB, hxA)), b1 = mul(dzB, sub(hyB, hyA));
+                const T b2 = mul(cb.cys, sub(hxynB, hxB)), b3 = mul(cb.cys, sub(hzynB, hzB));
+                const T b4 = mul(cb.cxs, sub(hyxnB, hyB)), b5 = mul(cb.cxs, sub(hzxnB, hzB));
+                stg_stream(p.G[0] + off_out + sz, ADD ? add(add(gB0, neg(b1)), b3) : add(add(Z, neg(b1)), b3));
+                stg_stream(p.G[1] + off_out + sz, ADD ? add(add(gB1, b0), neg(b5)) : add(b0, neg(b5)));
+                stg_stream(p.G[2] + off_out + sz, ADD ? add(add(gB2, neg(b2)), b4) : add(neg(b2), b4));
+            }
+            bxlo = hxB;
+            bylo = hyB;
+            {   // H slot 2t−1
+                const T a0 = mul(czA, sub(xB, axlo)), a1 = mul(czA, sub(yB, aylo));
+                const T a2 = mul(ca.cys, sub(xynA, axlo)), a3 = mul(ca.cys, sub(zynA, zA));
+                const T a4 = mul(ca.cxs, sub(yxnA, aylo)), a5 = mul(ca.cxs, sub(zxnA, zA));
+                sts_at<0>(out, add(add(Z, neg(a1)), a3));
+                sts_at<HCB>(out, add(a0, neg(a5)));
+                sts_at<2 * HCB>(out, add(neg(a2), a4));
+            }
+            {   // H slot 2t
+                const T b0 = mul(czB, sub(xC, xB)), b1 = mul(czB, sub(yC, yB));
+                const T b2 = mul(ca.cys, sub(xynB, xB)), b3 = mul(ca.cys, sub(zynB, zB));
+                const T b4 = mul(ca.cxs, sub(yxnB, yB)), b5 = mul(ca.cxs, sub(zxnB, zB));
+                sts_at<HSTAGE>(out, add(add(Z, neg(b1)), b3));
+                sts_at<HSTAGE + HCB>(out, add(b0, neg(b5)));
+                sts_at<HSTAGE + 2 * HCB>(out, add(neg(b2), b4));
+            }
+            axlo = xC;
+            aylo = yC;
+            off_out += 2 * sz;
+            st_prev = st_cur;
+            if (++st_cur == NP) { st_cur = 0; e_phase ^= 1u; }
+            h_wr ^= 2u * HSTAGE;
+            __syncthreads();
+            continue;
+        }
+        if (SP == 1 && tile_plain && roleD && t >= 2 && t <= Th && k0 + 2 * t - 4 >= 1 && k0 + 2 * t - 1 <= Nz - 2 && 2 * t - 3 < n) {
             const C czA = lds_at<0>(sC1 + (unsigned)(2 * t) * CS, C{}), czB = lds_at<CS>(sC1 + (unsigned)(2 * t) * CS, C{});
             const C dzA = lds_at<0>(sC2 + (unsigned)(2 * t - 4) * CS, C{}), dzB = lds_at<CS>(sC2 + (unsigned)(2 * t - 4) * CS, C{});
             T gA0 = Z, gA1 = Z, gA2 = Z, gB0 = Z, gB1 = Z, gB2 = Z;

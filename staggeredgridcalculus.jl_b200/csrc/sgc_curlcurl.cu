@@ -113,7 +113,7 @@ int launch_cc5_tiles(const CurlCurl4Params<C> &P, int ty, int se, dim3 grid, cud
 }
 
 // ---- sixth generation (sgc_cc6.cuh): two planes per barrier interval; C₁ forward / C₂ backward in z only ----------------
-template <typename C, bool ADD, int TY, int NP, int MINB, bool SP>
+template <typename C, bool ADD, int TY, int NP, int MINB, int SP>
 int launch_cc6_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = cc6_smem_bytes(TY, NP);
     auto kern = k_cc6<C, ADD, TY, NP, MINB, SP>;
@@ -122,15 +122,16 @@ int launch_cc6_one(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
     kern<<<grid, dim3(32 * (TY + 1), 1, 1), smem, st>>>(P);
     return SGC_OK;
 }
-// sp: software-pipelined steady state
+// sp: steady state of boundary-free tiles — 0 two-phase code, 1 one straight-line block (H points first), 2 outputs first
 template <typename C, bool ADD>
 int launch_cc6_tiles(const CurlCurl4Params<C> &P, int ty, int np, int sp, dim3 grid, cudaStream_t st) {
-#define CC6_CASE(TY, NP, MINB, SP) if (ty == TY && np == NP && sp == SP) return launch_cc6_one<C, ADD, TY, NP, MINB, SP != 0>(P, grid, st);
-    CC6_CASE(5, 3, 2, 1)
+#define CC6_CASE(TY, NP, MINB, SP) if (ty == TY && np == NP && sp == SP) return launch_cc6_one<C, ADD, TY, NP, MINB, SP>(P, grid, st);
+    CC6_CASE(5, 3, 2, 2)
 #ifdef SGC_SWEEP_BUILD
+    CC6_CASE(5, 3, 2, 1)
     CC6_CASE(5, 3, 2, 0)
-    CC6_CASE(11, 3, 1, 1)
-    CC6_CASE(4, 4, 2, 1)
+    CC6_CASE(11, 3, 1, 2)
+    CC6_CASE(4, 4, 2, 2)
 #endif
 #undef CC6_CASE
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v6): tile 32x%d with %d pair stages, pipelining %d is not built", ty, np, sp);
@@ -300,8 +301,10 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
                     P.q.march = c2->march > 0 ? std::min<int>(c2->march, CC6_MAXMARCH) : cc6_march(tiles6, nk);
                     dim3 g6((unsigned)((p.Nx + 31) / 32), (unsigned)((p.Ny + ty6 - 1) / ty6), (unsigned)((nk + P.q.march - 1) / P.q.march));
                     if (g6.y > 65535 || g6.z > 65535) return sgc_fail(SGC_ERR_INVALID, "grid too large for the fused curl-of-curl tiling");
-                    // variant bits 8-11: 0 = default (software-pipelined steady state), 1 = two-phase code only
-                    const int sp6 = ((c2->variant >> 8) & 0xF) == 1 ? 0 : 1;
+                    // variant bits 8-11, steady state of boundary-free tiles: 0 = default (one straight-line block, outputs first),
+                    // 1 = two-phase code only, 2 = one block, H points first
+                    const int vsp = (c2->variant >> 8) & 0xF;
+                    const int sp6 = vsp == 1 ? 0 : (vsp == 2 ? 1 : 2);
                     s6 = add_mode ? launch_cc6_tiles<C, true>(P, ty6, np6, sp6, g6, st) : launch_cc6_tiles<C, false>(P, ty6, np6, sp6, g6, st);
                     if (s6) return s6;
                     return sgc_check_launch("k_cc6");

@@ -34,8 +34,8 @@ for bl in BCS:
     # ver 4: TMA-fed warp-specialised kernel (se = E stages | H stages << 4), ver 2: third generation (warp roles, cp.async)
     cfgs = [(0, 7, 4, 5, m) for m in (0, 32, 128)] + [(0, 7, 3, 5, 0), (0, 5, 4, 5, 0), (0, 5, 4, 5, 32)] + [(0, 6, 0, 4, 0), (32, 7, 3, 2, 64)]
     if len(sys.argv) > 2 and sys.argv[2] == "v6":  # ver 6: two planes per barrier interval (se = E pair stages)
-        # se low nibble = E pair stages, high nibble: 1 = two-phase code only (no software-pipelined steady state)
-        cfgs = [(0, 5, 3, 6, 32), (0, 5, 3 + 16, 6, 32), (0, 5, 3, 6, 64), (0, 11, 3, 6, 32), (0, 4, 4, 6, 32), (0, 5, 4, 5, 32)]
+        # se low nibble = E pair stages, high nibble: 0 = default (one block, outputs first), 1 = two-phase code only, 2 = one block, H points first
+        cfgs = [(0, 5, 3, 6, 0), (0, 5, 3 + 32, 6, 0), (0, 5, 3, 6, 32), (0, 5, 3 + 32, 6, 32), (0, 5, 3 + 16, 6, 32), (0, 5, 4, 5, 32)]
     if len(sys.argv) > 2 and sys.argv[2] == "v6march":
         cfgs = [(0, 5, 3, 6, m) for m in (20, 22, 24, 26, 28, 32, 38, 44, 52, 64)]
     if len(sys.argv) > 2 and sys.argv[2] == "quick":
