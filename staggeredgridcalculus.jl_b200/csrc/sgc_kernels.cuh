@@ -301,8 +301,11 @@ __global__ void __launch_bounds__(256) k_term_x(const __grid_constant__ TermPara
 
 // Operator along a strided axis (inner > 1): each thread owns VEC consecutive x of R consecutive
 // rows along the operator axis and keeps them in registers, so R outputs cost R+1 row loads.
+// (accumulating calls run with R = 2, and they and the weighted means with three resident CTAs per SM — measured; the arithmetic mean
+// and ∂ `=` forms are faster unconstrained —, the read-modify-write loads of G issued together with
+// the loads of F: 8192² Float64 m̂y `+=` 0.32 → see profiles/r2_time_2d_vec.jsonl)
 template <typename T, typename C, int KIND, bool ADD, int VEC, int R>
-__global__ void __launch_bounds__(256) k_term_s(const __grid_constant__ TermParams<T, C> p) {
+__global__ void __launch_bounds__(256, ((R <= 2 || KIND == KIND_MEAN_WEIGHTED) ? 3 : 0)) k_term_s(const __grid_constant__ TermParams<T, C> p) {
     const int64_t Nw = p.Nw, inner = p.inner;
     const int64_t x = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC;
     if (x >= inner) return;
@@ -326,6 +329,12 @@ __global__ void __launch_bounds__(256) k_term_s(const __grid_constant__ TermPara
                     for (int e = 0; e < VEC; ++e) V[q][e] = Z;
                 }
             }
+            T old[ADD ? R : 1][VEC];  // read-modify-write: the old values of G travel with the loads of F, not behind the arithmetic
+            if (ADD) {
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    if (i0 + r < p.i_end) ldg_vec_plain<T, VEC>(old[ADD ? r : 0], p.G + (o * Nw + i0 + r) * inner + x);
+            }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const int64_t i = i0 + r;
@@ -344,10 +353,8 @@ __global__ void __launch_bounds__(256) k_term_s(const __grid_constant__ TermPara
                     out[e] = term_eval_c<T, C, KIND>(p, i, fwd ? V[r][e] : V[r + 1][e], fwd ? V[r + 1][e] : V[r][e], ci, wi, wn);
                 T *g = p.G + (o * Nw + i) * inner + x;
                 if (ADD) {
-                    T old[VEC];
-                    ldg_vec_plain<T, VEC>(old, g);
 #pragma unroll
-                    for (int e = 0; e < VEC; ++e) out[e] = add(old[e], out[e]);
+                    for (int e = 0; e < VEC; ++e) out[e] = add(old[ADD ? r : 0][e], out[e]);
                 }
                 stg_vec_stream<T, VEC>(g, out);
             }

@@ -474,7 +474,8 @@ static int launch_term(const sgc_op *op, const Term &t, T *G, const T *F, const 
                 const int by = 256 / bx;
                 vblock = dim3(bx, by, 1);
                 vgrid.x = (unsigned)((p.inner / vec + bx - 1) / bx);
-                vgrid.y = (unsigned)std::min<int64_t>((p.i_end - p.i_begin + (int64_t)by * R - 1) / ((int64_t)by * R), 65535);
+                const int64_t rs = add_mode ? 2 : R;  // rows per thread of the strided kernel
+                vgrid.y = (unsigned)std::min<int64_t>((p.i_end - p.i_begin + (int64_t)by * rs - 1) / ((int64_t)by * rs), 65535);
                 vgrid.z = (unsigned)std::min<int64_t>(p.o_end - p.o_begin, 65535);
             }
 #define LAUNCH_VEC(KERN, KIND, VEC)                                                            \
@@ -488,8 +489,21 @@ static int launch_term(const sgc_op *op, const Term &t, T *G, const T *F, const 
                 case KIND_MEAN_ARITH: LAUNCH_VEC(KERN, KIND_MEAN_ARITH, VEC); break;            \
                 default: LAUNCH_VEC(KERN, KIND_MEAN_WEIGHTED, VEC); break;                      \
             }
+#define LAUNCH_STRIDED(KIND, VEC)                                                               \
+            do {                                                                                \
+                if (add_mode) k_term_s<T, C, KIND, true, VEC, 2><<<vgrid, vblock, 0, st>>>(p);   \
+                else k_term_s<T, C, KIND, false, VEC, R><<<vgrid, vblock, 0, st>>>(p);           \
+            } while (0)
+#define LAUNCH_STRIDED_KIND(VEC)                                                                \
+            switch (t.kind) {                                                                   \
+                case KIND_PARTIAL: LAUNCH_STRIDED(KIND_PARTIAL, VEC); break;                    \
+                case KIND_MEAN_ARITH: LAUNCH_STRIDED(KIND_MEAN_ARITH, VEC); break;              \
+                default: LAUNCH_STRIDED(KIND_MEAN_WEIGHTED, VEC); break;                        \
+            }
             if (xax) { if (vec == VBIG) { LAUNCH_VEC_KIND(k_term_x, VBIG) } else { LAUNCH_VEC_KIND(k_term_x, VSMALL) } }
-            else     { if (vec == VBIG) { LAUNCH_VEC_KIND(k_term_s, VBIG) } else { LAUNCH_VEC_KIND(k_term_s, VSMALL) } }
+            else     { if (vec == VBIG) { LAUNCH_STRIDED_KIND(VBIG) } else { LAUNCH_STRIDED_KIND(VSMALL) } }
+#undef LAUNCH_STRIDED_KIND
+#undef LAUNCH_STRIDED
 #undef LAUNCH_VEC_KIND
 #undef LAUNCH_VEC
             return check_launch(xax ? "k_term_x" : "k_term_s");
