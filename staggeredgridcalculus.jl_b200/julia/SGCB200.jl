@@ -332,6 +332,12 @@ function peer_array(comm::Ptr{Cvoid}, ::Type{T}, dims::Vararg{Int,N}) where {T,N
     return a
 end
 peer_barrier(comm::Ptr{Cvoid}) = check(ccall((:sgc_peer_barrier, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), comm, C_NULL))
+# device-side waits on a neighbour that gave up (0 in a correct run; synchronises the default stream)
+function comm_timeouts(comm::Ptr{Cvoid})
+    n = Ref{Int64}(0)
+    check(ccall((:sgc_comm_timeouts, LIB), Cint, (Ptr{Cvoid}, Ref{Int64}, Ptr{Cvoid}), comm, n, C_NULL))
+    return n[]
+end
 
 # ---------------------------------------------------------------------------------------------
 # sparse assembly: handle → shape → colptr (count + scan) → fill → SparseMatrixCSC
