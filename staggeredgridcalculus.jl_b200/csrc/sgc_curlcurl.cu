@@ -14,6 +14,12 @@ using namespace sgc;
 
 namespace {
 
+#ifdef SGC_SWEEP_BUILD
+constexpr bool kCcExperiments = true;
+#else
+constexpr bool kCcExperiments = false;
+#endif
+
 // ---- fourth generation (sgc_cc4.cuh): TMA-fed, warp-specialised ----------------------------------------------------
 // cuTensorMapEncodeTiled comes from the driver; the library links the runtime only, so the entry point is looked up.
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -79,10 +85,13 @@ int launch_cc4_dirs(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
 }
 template <typename C, bool ADD>
 int launch_cc4_tiles(const CurlCurl4Params<C> &P, int ty, int se, int sh, dim3 grid, cudaStream_t st) {
+#ifdef SGC_SWEEP_BUILD
 #define CC4_CASE(TY, SE, SH) if (ty == TY && se == SE && sh == SH) return launch_cc4_dirs<C, ADD, TY, SE, SH>(P, grid, st);
     CC4_CASE(6, 4, 3)
     CC4_CASE(8, 4, 3)
 #undef CC4_CASE
+#endif
+    (void)P; (void)grid; (void)st;
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (TMA): tile 32x%d with %d/%d stages is not built", ty, se, sh);
 }
 
@@ -104,11 +113,14 @@ int launch_cc5_dirs(const CurlCurl4Params<C> &P, dim3 grid, cudaStream_t st) {
 }
 template <typename C, bool ADD>
 int launch_cc5_tiles(const CurlCurl4Params<C> &P, int ty, int se, dim3 grid, cudaStream_t st) {
+#ifdef SGC_SWEEP_BUILD
 #define CC5_CASE(TY, SE) if (ty == TY && se == SE) return launch_cc5_dirs<C, ADD, TY, SE>(P, grid, st);
     CC5_CASE(7, 3)
     CC5_CASE(7, 4)
     CC5_CASE(5, 4)
 #undef CC5_CASE
+#endif
+    (void)P; (void)grid; (void)st;
     return sgc_fail(SGC_ERR_INVALID, "fused curl-of-curl (v5): tile 32x%d with %d stages is not built", ty, se);
 }
 
@@ -312,7 +324,9 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
                 // no tensor-map support in this driver: fall through to the third generation
             }
         }
-        if (version == 5 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= 9) {
+        // (k_cc4 / k_cc5 are measured experiments, built with `make EXTRA=-DSGC_SWEEP_BUILD`; the product library runs the third
+        // generation when they are asked for)
+        if (kCcExperiments && version == 5 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= 9) {
             const int ty5 = (c2->tile_y == 5) ? 5 : 7;
             const int se5 = (((c2->variant >> 4) & 0xF) == 3 && ty5 == 7) ? 3 : 4;
             CurlCurl4Params<C> P{};
@@ -328,7 +342,7 @@ int launch_cc(const sgc_op *c2, const sgc_op *c1, T *G, const T *F, bool add_mod
                 return sgc_check_launch("k_cc5");
             }
         }
-        if (version == 4 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= ty4 + 2) {
+        if (kCcExperiments && version == 4 && !wraps_xy && !ghosts && p.Nx >= 34 && p.Ny >= ty4 + 2) {
             CurlCurl4Params<C> P{};
             P.q = p;
             int s4 = SGC_OK;

@@ -448,7 +448,9 @@ def test_fused_divg_grad_slab_split_equals_whole(S):
 # (tile_x, tile_y, march, ring stages, kernel version): version 0 / 2 = third generation (warp roles, cp.async; the
 # default), 1 = first generation, 4 = the TMA-fed warp-specialised experiment k_cc4 where it applies (ComplexF64, no Bloch
 # wrap in x / y, no slab ghosts; tile_y 6 or 8), else the third generation; 5 = k_cc5; 6 = k_cc6 (two planes per barrier interval;
-# C1 forward / C2 backward in z, ring stages = E pair stages), else the third generation
+# C1 forward / C2 backward in z, ring stages = E pair stages), else the third generation.  k_cc4 / k_cc5 are measured experiments that
+# only a `make EXTRA=-DSGC_SWEEP_BUILD` library carries; the product library answers versions 4 / 5 with the third generation, so
+# these tilings then exercise that routing.
 CURLCURL_TILINGS = [(0, 0, 0, 0, 0), (32, 7, 3, 3, 2), (32, 7, 5, 4, 2), (32, 4, 2, 4, 2), (32, 7, 1, 3, 2), (32, 4, 7, 4, 2),
                     (32, 8, 3, 3, 1), (32, 8, 2, 3, 1), (32, 8, 6, 3, 1),
                     (0, 6, 3, 0, 4), (0, 8, 1, 0, 4), (0, 6, 0, 0, 4), (0, 7, 3, 4, 5), (0, 7, 1, 3, 5), (0, 5, 2, 4, 5), (0, 7, 0, 0, 5),
