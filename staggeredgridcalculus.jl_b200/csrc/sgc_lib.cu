@@ -466,7 +466,13 @@ static int launch_term(const sgc_op *op, const Term &t, T *G, const T *F, const 
             if (xax) {
                 vblock = dim3(256, 1, 1);
                 vgrid.x = (unsigned)((p.Nw / vec + 255) / 256);
-                vgrid.y = (unsigned)std::min<int64_t>((p.o_end - p.o_begin + R - 1) / R, 65535);
+                // a thread keeps the table entries of its VEC elements in registers and walks down the rows: enough CTAs to
+                // fill the GPU a few times over (op->march: CTAs per SM, default 24; 8 for accumulating weighted means), not one CTA per R rows, so that the
+                // table loads are shared by many rows (8192² Float64 weighted m̂x: see profiles/r2_time_2d_vec.jsonl)
+                const int64_t rowblocks = (p.o_end - p.o_begin + R - 1) / R;
+                const int per_sm = op->march > 0 ? op->march : ((add_mode && t.kind == KIND_MEAN_WEIGHTED) ? 8 : 24);
+                const int64_t want = ((int64_t)148 * per_sm + vgrid.x - 1) / vgrid.x;
+                vgrid.y = (unsigned)std::min<int64_t>(std::min<int64_t>(rowblocks, std::max<int64_t>(want, 1)), 65535);
                 vgrid.z = 1;
             } else {
                 int bx = 32;

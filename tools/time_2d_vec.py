@@ -14,6 +14,7 @@ def timeit(fn, iters=10, warm=3):
     return a.elapsed_time(b) / iters
 
 n = 8192
+MARCH = int(sys.argv[1]) if len(sys.argv) > 1 else 0  # x-axis kernel: CTAs per SM (0 = default)
 N = (n, n); M = n * n
 rng = np.random.default_rng(0)
 F = S.DeviceArray(torch.rand(M, device="cuda", dtype=torch.float64), N)
@@ -28,7 +29,7 @@ for nw in (1, 2):
             for op, B in (("=", 16), ("+=", 24)):
                 row = dict(op=name, nw=nw, fwd=fwd, mode=op)
                 for v in (0, 4, 5):
-                    o.set_tuning(0, 0, 0, v)
+                    o.set_tuning(0, 0, MARCH, v)
                     ms = timeit(lambda: o.apply(G, F, op))
                     row[f"v{v}_ms"] = round(ms, 4); row[f"v{v}_gbs"] = round(B * M / ms / 1e6)
                 print(json.dumps(row), flush=True)
