@@ -79,7 +79,10 @@ int sgc_launch_curl3(const sgc_op *op, T *G, const T *F, const void *const *ghos
     if (!stages) stages = (tx == 32 && ty == 4) ? 6 : 4;  // 6-stage ring: 4 planes in flight per CTA, 47.5 KB, 4 CTAs/SM
     int minb = (op->variant >> 8) & 0xF;
     if (!minb) minb = (tx * ty <= 128) ? 4 : ((tx * ty <= 256) ? 3 : 2);
-    const bool xshfl = ((op->variant >> 12) & 1) == 0;  // bit 12: read x-neighbours from the shared tile instead
+    // x-neighbours from the shared tile (default) or by warp shuffle (bit 12).  Cold the two are within 1 %; in the sustained,
+    // power-capped state the benchmark boxes settle into (≈ 1.65 of 1.97 GHz) the shared-tile form, with fewer instructions per
+    // plane, is ≈ 3 % faster (tools/time_curl_xshfl.py, profiles/r2_time_curl_xshfl.jsonl)
+    const bool xshfl = ((op->variant >> 12) & 1) != 0;
     int s = add_mode ? launch_curl3p_tiles<T, C, true>(p, tx, ty, stages, minb, xshfl, grid, st)
                      : launch_curl3p_tiles<T, C, false>(p, tx, ty, stages, minb, xshfl, grid, st);
     if (s) return s;
